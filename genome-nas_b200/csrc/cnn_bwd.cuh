@@ -1,0 +1,591 @@
+// Backward kernels of the MixedOp / CNN cell path (fp32).  The identities used
+// are those autograd derives for the reference modules:
+// for a candidate ending in BN without affine, with upstream gradient g,
+//   S1_c = sum g, S2_c = sum g*zhat,  dmix_k = sum_c S2_c,
+//   dz   = (w/sigma_c) * (g - S1_c/n - zhat*S2_c/n)  =  A_c*g + Bz_c*z + D_c
+// so every consumer reads (g, z) and three per-channel coefficients.
+#pragma once
+#include "common.cuh"
+#include "cnn_fwd.cuh"
+
+namespace gnas {
+
+// ------------------------------------------------------------------ reductions for BN backward / dmix
+struct RedTerm {
+  const float* z; long long bs;   // forward tensor (raw pre-BN output, or x for the identity skip)
+  const float* mask;              // dropout mask of the identity skip or null
+  int slot;                       // backward accumulator slot, or -1 for the identity skip
+  int widx;                       // mixing weight index (identity skip: dmix accumulates directly)
+};
+struct RedBatch {
+  int B, C, L, nterms, s1_slot;   // s1_slot: where sum(g) goes (shared by all terms), -1: per term slot only
+  const float* g; long long gbs;
+  double* bacc;                   // [slot][2][C]
+  double* dmix;                   // [n_edges*n_prims]
+  RedTerm t[kMaxTerms];
+};
+
+// CTA: channel c, 8 batch rows (one per warp).  bacc[slot] = (sum g, sum g*z)
+static __global__ void __launch_bounds__(kThreads) k_bwd_reduce(const __grid_constant__ RedBatch P) {
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 8 + warp;
+  __shared__ float red[8];
+  const bool ok = b < P.B;
+  const float* gr = P.g + (long long)(ok ? b : 0) * P.gbs + (long long)c * P.L;
+  float s1 = 0.f;
+  if (ok) for (int l = lane; l < P.L; l += 32) s1 += gr[l];
+  s1 = warp_sum(s1);
+  if (lane == 0) red[warp] = s1;
+  __syncthreads();
+  double S1 = 0.0;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 8; ++w) S1 += (double)red[w];
+    if (P.s1_slot >= 0) atomicAdd(&P.bacc[(long long)P.s1_slot * 2 * P.C + c], S1);
+  }
+  for (int t = 0; t < P.nterms; ++t) {
+    const RedTerm& T = P.t[t];
+    float s2 = 0.f;
+    if (ok) {
+      const float* zr = T.z + (long long)b * T.bs + (long long)c * P.L;
+      if (T.mask) {
+        const float* mr = T.mask + ((long long)b * P.C + c) * P.L;
+        for (int l = lane; l < P.L; l += 32) s2 = fmaf(gr[l], zr[l] * mr[l], s2);
+      } else {
+        for (int l = lane; l < P.L; l += 32) s2 = fmaf(gr[l], zr[l], s2);
+      }
+    }
+    s2 = warp_sum(s2);
+    __syncthreads();
+    if (lane == 0) red[warp] = s2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double S2 = 0.0;
+      for (int w = 0; w < 8; ++w) S2 += (double)red[w];
+      if (T.slot >= 0) {
+        double* a = P.bacc + (long long)T.slot * 2 * P.C;
+        if (P.s1_slot < 0) atomicAdd(&a[c], S1);
+        atomicAdd(&a[P.C + c], S2);
+      } else {
+        atomicAdd(&P.dmix[T.widx], S2);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ coefficients A | Bz | D
+struct CoefBatch {
+  const double* bacc; const float* stat; float* coef;   // indexed by slot
+  const float* mixw; double* dmix;
+  const float* gamma; float* dgamma; float* dbeta;      // affine BN (stem) or null
+  int C, nslots, s1_slot;                               // s1_slot >= 0: sum(g) lives in that slot
+  short slot[kMaxSlots]; short widx[kMaxSlots]; float count[kMaxSlots];
+};
+
+static __global__ void k_bn_bwd_coef(const __grid_constant__ CoefBatch P) {
+  const int s = P.slot[blockIdx.x];
+  const int wi = P.widx[blockIdx.x];
+  const double n = (double)P.count[blockIdx.x];
+  const double w = wi >= 0 ? (double)P.mixw[wi] : 1.0;
+  const double* a = P.bacc + (long long)s * 2 * P.C;
+  const double* a1 = P.s1_slot >= 0 ? P.bacc + (long long)P.s1_slot * 2 * P.C : a;
+  const float* st = P.stat + (long long)s * 2 * P.C;
+  float* cf = P.coef + (long long)s * 3 * P.C;
+  __shared__ double red[32];
+  double part = 0.0;
+  for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
+    const double mean = st[c], rstd = st[P.C + c];
+    const double S1 = a1[c];
+    const double S2 = rstd * (a[P.C + c] - mean * S1);
+    const double wc = P.gamma ? w * (double)P.gamma[c] : w;
+    cf[c] = (float)(wc * rstd);
+    cf[P.C + c] = (float)(-wc * rstd * rstd * S2 / n);
+    cf[2 * P.C + c] = (float)(-wc * rstd * S1 / n + wc * rstd * rstd * mean * S2 / n);
+    if (P.dgamma) { P.dgamma[c] += (float)S2; P.dbeta[c] += (float)S1; }
+    part += S2;
+  }
+  part = warp_sum_d(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0 && wi >= 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x + 31) / 32; ++i) t += red[i];
+    atomicAdd(&P.dmix[wi], t);
+  }
+}
+
+// ------------------------------------------------------------------ transposed dense conv (data gradient)
+struct DxJob {
+  const float* g; long long gbs;     // upstream gradient [B][Cout][Lo]
+  const float* z; long long zbs;     // raw forward output of the BN being differentiated, or null
+  const float* coef;                 // A | Bz | D  [3][Cout]
+  const float* wt;                   // packed [Cout][KW][Cin]
+  float* out; long long obs;         // [B][Cin][Lin]
+  const float* xin; long long xibs;  // forward input: x (O_RELU_ACC) or z1 (O_BNRELU_STORE)
+  const float* xin_stat;             // mean | rstd of the inner BN
+  double* bacc;                      // (sum v, sum v*z1)[Cin]
+  int Cout, Lo, Lin, omode;
+};
+struct DxBatch { int n, B, Cin, nq, pad, KC; DxJob j[kMaxDense]; };
+
+// out[b,ci,m] (op)= sum_{co,t : (m+pad-t)%S==0} W[co,ci,t] * dz[b,co,(m+pad-t)/S]
+template <int KW, int S, int TM>
+__global__ void __launch_bounds__(kThreads) k_dense_bwd_dx(const __grid_constant__ DxBatch P) {
+  const DxJob& J = P.j[blockIdx.z];
+  const int nq = P.nq, TLm = 4 * S * nq, m0 = blockIdx.x * TLm;
+  if (m0 >= J.Lin) return;
+  const int b = blockIdx.y, Cin = P.Cin, KC = P.KC;
+  const int ncig = Cin / TM;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cig = tid / (S * nq), rem = tid - cig * (S * nq);
+  const int rho = rem / nq, q = rem - rho * nq;
+  const bool active = cig < ncig;
+  constexpr int NT = (KW + S - 1) / S;           // max taps per residue class
+  constexpr int NXW = 4 + NT;                    // window (incl. +1 for the residue shift)
+  constexpr int NX4 = (NXW + 3) / 4;
+  const int t0 = (rho + P.pad) % S;
+  const int nt = t0 < KW ? (KW - t0 + S - 1) / S : 0;
+  const int dc = (rho + P.pad - t0) / S - P.pad / S;   // 0 or 1
+  const int lbase = m0 / S + P.pad / S - (NT - 1);
+  const int Wu = 4 * nq + NT + 1;
+  const int Wp = (Wu + 3) / 4 * 4 + 4;
+  GNAS_DYN_SMEM(float, smem);
+  float* ds = smem;                               // [KC][Wp]  dz tile
+  float* ws = ds + KC * Wp;                       // [KC][KW][Cin]
+  float* ssum = ws + KC * KW * Cin;               // [2][Cin]
+  for (int i = tid; i < 2 * Cin; i += kThreads) ssum[i] = 0.f;
+  float acc[TM][4];
+#pragma unroll
+  for (int m = 0; m < TM; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[m][n] = 0.f;
+  for (int c0 = 0; c0 < J.Cout; c0 += KC) {
+    for (int co = warp; co < KC; co += kThreads / 32) {
+      const float* gr = J.g + (long long)b * J.gbs + (long long)(c0 + co) * J.Lo;
+      const float* zr = J.z ? J.z + (long long)b * J.zbs + (long long)(c0 + co) * J.Lo : nullptr;
+      float A = 1.f, Bz = 0.f, D = 0.f;
+      if (zr) { A = J.coef[c0 + co]; Bz = J.coef[J.Cout + c0 + co]; D = J.coef[2 * J.Cout + c0 + co]; }
+      for (int p = lane; p < Wp; p += 32) {
+        const int l = lbase + p;
+        float v = 0.f;
+        if (p < Wu && l >= 0 && l < J.Lo) v = zr ? fmaf(A, gr[l], fmaf(Bz, zr[l], D)) : gr[l];
+        ds[co * Wp + p] = v;
+      }
+    }
+    {
+      const float4* src = reinterpret_cast<const float4*>(J.wt + (long long)c0 * KW * Cin);
+      float4* dst = reinterpret_cast<float4*>(ws);
+      const int n4 = KC * KW * Cin / 4;
+      for (int i = tid; i < n4; i += kThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (active && nt > 0) {
+      for (int co = 0; co < KC; ++co) {
+        float xr[NX4 * 4];
+        if (S == 1) {
+          const float4* xp = reinterpret_cast<const float4*>(ds + co * Wp + 4 * q);
+#pragma unroll
+          for (int k = 0; k < NX4; ++k) { float4 v = xp[k]; xr[4 * k] = v.x; xr[4 * k + 1] = v.y; xr[4 * k + 2] = v.z; xr[4 * k + 3] = v.w; }
+        } else {
+          const float* xp = ds + co * Wp + 4 * q + dc;
+#pragma unroll
+          for (int k = 0; k < NXW - 1; ++k) xr[k] = xp[k];
+        }
+        const float* wrow = ws + co * KW * Cin + cig * TM;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          if (t < nt) {
+            float w[TM];
+            WVec<TM>::ld(wrow + (t0 + S * t) * Cin, w);
+#pragma unroll
+            for (int m = 0; m < TM; ++m)
+#pragma unroll
+              for (int n = 0; n < 4; ++n) acc[m][n] = fmaf(w[m], xr[n + NT - 1 - t], acc[m][n]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- epilogue
+  const bool pow2 = (nq & (nq - 1)) == 0;
+  const int width = nq < 32 ? nq : 32;
+#pragma unroll
+  for (int m = 0; m < TM; ++m) {
+    const int ci = cig * TM + m;
+    float s = 0.f, qq = 0.f;
+    if (active && (nt > 0 || J.omode == O_STORE || J.omode == O_BNRELU_STORE)) {
+      float* orow = J.out + (long long)b * J.obs + (long long)ci * J.Lin;
+      const float* xrow = J.xin ? J.xin + (long long)b * J.xibs + (long long)ci * J.Lin : nullptr;
+      const float mean = (J.omode == O_BNRELU_STORE) ? J.xin_stat[ci] : 0.f;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int pos = m0 + S * (4 * q + n) + rho;
+        if (pos < J.Lin) {
+          const float v = acc[m][n];
+          if (J.omode == O_STORE) orow[pos] = v;
+          else if (J.omode == O_ACC) orow[pos] += v;
+          else if (J.omode == O_RELU_ACC) { if (xrow[pos] > 0.f) orow[pos] += v; }
+          else {
+            const float zi = xrow[pos];
+            const float vv = zi > mean ? v : 0.f;
+            orow[pos] = vv; s += vv; qq = fmaf(vv, zi, qq);
+          }
+        }
+      }
+    }
+    if (J.omode == O_BNRELU_STORE) {
+      if (pow2 && S == 1) {
+        for (int o = width >> 1; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
+        if (active && (q & (width - 1)) == 0) { atomicAdd(&ssum[ci], s); atomicAdd(&ssum[Cin + ci], qq); }
+      } else if (active) {
+        atomicAdd(&ssum[ci], s); atomicAdd(&ssum[Cin + ci], qq);
+      }
+    }
+  }
+  if (J.omode == O_BNRELU_STORE) {
+    __syncthreads();
+    for (int i = tid; i < 2 * Cin; i += kThreads) atomicAdd(&J.bacc[i], (double)ssum[i]);
+  }
+}
+
+// ------------------------------------------------------------------ pointwise (1x1) weight gradient
+struct WgJob {
+  const float* g; long long gbs;     // upstream gradient [B][Cout][Lo]
+  const float* z; long long zbs;     // raw BN input (affine dz) or null
+  const float* coef;
+  const float* r; long long rbs;     // forward input of the conv [B][Cin][Lin]
+  const float* r_stat;               // for T_BN_RELU
+  float* dw;                         // [Cout][Cin][KW], accumulated with atomics
+  int Cin, Lo, Lin, tin;
+};
+struct WgBatch { int n, B, Cout, S, pad, BCH, TL, COB, CIB, G; WgJob j[kMaxDense]; };
+
+// dW[co,ci] += sum_{b,l} dz[b,co,l] * T(r)[b,ci,l*S]
+template <int TC>
+__global__ void __launch_bounds__(kThreads) k_pw_wgrad(const __grid_constant__ WgBatch P) {
+  const WgJob& J = P.j[blockIdx.z];
+  const int nbo = (P.Cout + P.COB - 1) / P.COB, nbi = (J.Cin + P.CIB - 1) / P.CIB;
+  const int wb = blockIdx.x;
+  if (wb >= nbo * nbi) return;
+  const int co0 = (wb / nbi) * P.COB, ci0 = (wb % nbi) * P.CIB;
+  const int cob = min(P.COB, P.Cout - co0), cib = min(P.CIB, J.Cin - ci0);
+  const int nco_t = cob / TC, nci_t = cib / TC;
+  const int tid = threadIdx.x;
+  const int per = nco_t * nci_t;
+  const int G = kThreads / per;
+  const int grp = tid / per, r2 = tid - grp * per;
+  const int cq = r2 / nci_t, iq = r2 - cq * nci_t;
+  const bool active = grp < G;
+  const int TL = P.TL;
+  const int po = P.COB + 4, pi = P.CIB + 4;
+  GNAS_DYN_SMEM(float, smem);
+  float* dzs = smem;             // [TL][po]
+  float* rs = dzs + TL * po;     // [TL][pi]
+  float acc[TC][TC];
+#pragma unroll
+  for (int i = 0; i < TC; ++i)
+#pragma unroll
+    for (int k = 0; k < TC; ++k) acc[i][k] = 0.f;
+  const int b0 = blockIdx.y * P.BCH, b1 = min(P.B, b0 + P.BCH);
+  for (int b = b0; b < b1; ++b) {
+    for (int l0 = 0; l0 < J.Lo; l0 += TL) {
+      const int nl = min(TL, J.Lo - l0);
+      for (int i = tid; i < cob * TL; i += kThreads) {
+        const int c = i / TL, l = i - c * TL;
+        float v = 0.f;
+        if (l < nl) {
+          const long long o = (long long)(co0 + c) * J.Lo + l0 + l;
+          const float gv = J.g[(long long)b * J.gbs + o];
+          v = J.z ? fmaf(J.coef[co0 + c], gv, fmaf(J.coef[P.Cout + co0 + c], J.z[(long long)b * J.zbs + o], J.coef[2 * P.Cout + co0 + c])) : gv;
+        }
+        dzs[l * po + c] = v;
+      }
+      for (int i = tid; i < cib * TL; i += kThreads) {
+        const int c = i / TL, l = i - c * TL;
+        float v = 0.f;
+        if (l < nl) {
+          const int pos = (l0 + l) * P.S;
+          float mean = 0.f, rstd = 1.f;
+          if (J.tin >= T_BN_RELU) { mean = J.r_stat[ci0 + c]; rstd = J.r_stat[J.Cin + ci0 + c]; }
+          v = apply_tin(J.r[(long long)b * J.rbs + (long long)(ci0 + c) * J.Lin + pos], J.tin, mean, rstd);
+        }
+        rs[l * pi + c] = v;
+      }
+      __syncthreads();
+      if (active) {
+        for (int l = grp; l < nl; l += G) {
+          float a[TC], bb[TC];
+#pragma unroll
+          for (int i = 0; i < TC; ++i) a[i] = dzs[l * po + cq * TC + i];
+#pragma unroll
+          for (int k = 0; k < TC; ++k) bb[k] = rs[l * pi + iq * TC + k];
+#pragma unroll
+          for (int i = 0; i < TC; ++i)
+#pragma unroll
+            for (int k = 0; k < TC; ++k) acc[i][k] = fmaf(a[i], bb[k], acc[i][k]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < TC; ++i)
+#pragma unroll
+      for (int k = 0; k < TC; ++k)
+        atomicAdd(&J.dw[(long long)(co0 + cq * TC + i) * J.Cin + ci0 + iq * TC + k], acc[i][k]);
+  }
+}
+
+// dW[co,ci,t] += sum_{b,l} dz[b,co,l] * T(r)[b,ci,l*S+t-pad]     (KW = 15 cells, 13 stem)
+template <int KW, int S>
+__global__ void __launch_bounds__(kThreads) k_conv_wgrad(const __grid_constant__ WgBatch P) {
+  const WgJob& J = P.j[blockIdx.z];
+  const int nbo = (P.Cout + P.COB - 1) / P.COB, nbi = (J.Cin + P.CIB - 1) / P.CIB;
+  const int wb = blockIdx.x;
+  if (wb >= nbo * nbi) return;
+  const int co0 = (wb / nbi) * P.COB, ci0 = (wb % nbi) * P.CIB;
+  const int cob = min(P.COB, P.Cout - co0), cib = min(P.CIB, J.Cin - ci0);
+  const int ncoq = cob / 4;
+  const int per = ncoq * cib;
+  const int G = kThreads / per;
+  const int tid = threadIdx.x;
+  const int grp = tid / per, r2 = tid - grp * per;
+  const int coq = r2 / cib, ci = r2 - coq * cib;
+  const bool active = grp < G;
+  const int TLg = P.TL;                 // positions per group per iteration
+  const int TLc = TLg * G;              // positions per CTA iteration
+  const int pz = TLc | 1;
+  const int Wr = (TLc - 1) * S + KW;
+  const int pr = Wr | 1;
+  GNAS_DYN_SMEM(float, smem);
+  float* dzs = smem;                    // [cob][pz]
+  float* rs = dzs + P.COB * pz;         // [cib][pr]
+  float acc[4][KW];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int t = 0; t < KW; ++t) acc[i][t] = 0.f;
+  const int b0 = blockIdx.y * P.BCH, b1 = min(P.B, b0 + P.BCH);
+  for (int b = b0; b < b1; ++b) {
+    for (int l0 = 0; l0 < J.Lo; l0 += TLc) {
+      const int nl = min(TLc, J.Lo - l0);
+      for (int i = tid; i < cob * TLc; i += kThreads) {
+        const int c = i / TLc, l = i - c * TLc;
+        float v = 0.f;
+        if (l < nl) {
+          const long long o = (long long)(co0 + c) * J.Lo + l0 + l;
+          const float gv = J.g[(long long)b * J.gbs + o];
+          v = J.z ? fmaf(J.coef[co0 + c], gv, fmaf(J.coef[P.Cout + co0 + c], J.z[(long long)b * J.zbs + o], J.coef[2 * P.Cout + co0 + c])) : gv;
+        }
+        dzs[c * pz + l] = v;
+      }
+      const int in0 = l0 * S - P.pad;
+      for (int i = tid; i < cib * Wr; i += kThreads) {
+        const int c = i / Wr, p = i - c * Wr;
+        const int pos = in0 + p;
+        float v = 0.f;
+        if (pos >= 0 && pos < J.Lin) {
+          float mean = 0.f, rstd = 1.f;
+          if (J.tin >= T_BN_RELU) { mean = J.r_stat[ci0 + c]; rstd = J.r_stat[J.Cin + ci0 + c]; }
+          v = apply_tin(J.r[(long long)b * J.rbs + (long long)(ci0 + c) * J.Lin + pos], J.tin, mean, rstd);
+        }
+        rs[c * pr + p] = v;
+      }
+      __syncthreads();
+      if (active) {
+        const int le = min(nl, (grp + 1) * TLg);
+        const float* rr = rs + ci * pr;
+        for (int l = grp * TLg; l < le; ++l) {
+          float d[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d[i] = dzs[(coq * 4 + i) * pz + l];
+#pragma unroll
+          for (int t = 0; t < KW; ++t) {
+            const float rv = rr[l * S + t];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][t] = fmaf(d[i], rv, acc[i][t]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int t = 0; t < KW; ++t)
+        atomicAdd(&J.dw[((long long)(co0 + coq * 4 + i) * J.Cin + ci0 + ci) * KW + t], acc[i][t]);
+  }
+}
+
+// ------------------------------------------------------------------ depthwise backward
+struct DwBwdJob {
+  const float* du; long long dubs;   // gradient wrt the depthwise output [B][C][Lo]
+  const float* x; long long xbs;     // forward input [B][C][Lin]
+  const float* in_stat;              // inner BN mean|rstd (T_BN_RELU)
+  const float* wd;                   // [C][K]
+  float* out; long long obs;         // dX accumulate (O_RELU_ACC) or dyh store (O_BNRELU_STORE)
+  double* bacc;                      // (sum v, sum v*z1)[C] for O_BNRELU_STORE
+  float* dwd;                        // [C][K] atomics, or null
+  int Lin, Lo, tin, omode;
+};
+struct DwBwdBatch { int n, B, C, pad, Wx, Wd; DwBwdJob j[kMaxDw]; };
+
+// CTA: channel c, 8 batch rows (one per warp)
+template <int K, int D, int S>
+__global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwBwdBatch P) {
+  const DwBwdJob& J = P.j[blockIdx.z];
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 8 + warp;
+  const bool ok = b < P.B;
+  GNAS_DYN_SMEM(float, smem);
+  float* xrow = smem + warp * (P.Wx + P.Wd);   // T(x) with zero halo: index p <-> pos = p - pad
+  float* drow = xrow + P.Wx;                   // du with zero halo: index i <-> l = i - K
+  __shared__ float red[8][K + 2];
+  float mean = 0.f, rstd = 1.f;
+  if (J.tin >= T_BN_RELU) { mean = J.in_stat[c]; rstd = J.in_stat[P.C + c]; }
+  const float* xg = J.x + (long long)(ok ? b : 0) * J.xbs + (long long)c * J.Lin;
+  if (ok) {
+    for (int p = lane; p < P.Wx; p += 32) {
+      const int pos = p - P.pad;
+      xrow[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xg[pos], J.tin, mean, rstd) : 0.f;
+    }
+    const float* dg = J.du + (long long)b * J.dubs + (long long)c * J.Lo;
+    for (int i = lane; i < P.Wd; i += 32) {
+      const int l = i - K;
+      drow[i] = (l >= 0 && l < J.Lo) ? dg[l] : 0.f;
+    }
+  }
+  __syncwarp();
+  float w[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) w[t] = J.wd[c * K + t];
+  float s = 0.f, qq = 0.f;
+  if (ok) {
+    float* orow = J.out + (long long)b * J.obs + (long long)c * J.Lin;
+    for (int m = lane; m < J.Lin; m += 32) {
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        const int num = m + P.pad - t * D;
+        if (S == 1) { a = fmaf(w[t], drow[num + K], a); }
+        else if (num >= 0 && num % S == 0) { a = fmaf(w[t], drow[num / S + K], a); }
+      }
+      const float xv = xg[m];
+      if (J.omode == O_RELU_ACC) { if (xv > 0.f) orow[m] += a; }
+      else { const float v = xv > mean ? a : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv, qq); }
+    }
+  }
+  // depthwise weight gradient: dwd[c,t] += sum_l du[l] * T(x)[l*S + t*D - pad]
+  float gw[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) gw[t] = 0.f;
+  if (ok && J.dwd) {
+    for (int l = lane; l < J.Lo; l += 32) {
+      const float dv = drow[l + K];
+#pragma unroll
+      for (int t = 0; t < K; ++t) gw[t] = fmaf(dv, xrow[l * S + t * D], gw[t]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < K; ++t) { gw[t] = warp_sum(gw[t]); if (lane == 0) red[warp][t] = gw[t]; }
+  s = warp_sum(s); qq = warp_sum(qq);
+  if (lane == 0) { red[warp][K] = s; red[warp][K + 1] = qq; }
+  __syncthreads();
+  if (threadIdx.x < K + 2) {
+    float t = 0.f;
+    for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+    if (threadIdx.x < K) { if (J.dwd) atomicAdd(&J.dwd[c * K + threadIdx.x], t); }
+    else if (J.omode == O_BNRELU_STORE) atomicAdd(&J.bacc[(threadIdx.x - K) * P.C + c], (double)t);
+  }
+}
+
+// ------------------------------------------------------------------ pools + identity skip backward
+struct PoolBwdJob {
+  const float* g; long long gbs;       // node gradient [B][C][Lo]
+  const float* x; long long xbs;       // edge input [B][C][Lin]
+  const float* zmax; const float* zavg;   // raw pool outputs (contiguous [B][C][Lo]) or null
+  const float* coef_max; const float* coef_avg;
+  const float* skip_mask;              // dropout mask or null
+  float* dx; long long dxbs;           // accumulated
+  int Lin, Lo, skip_widx;              // skip_widx < 0: no identity skip on this edge
+};
+struct PoolBwdBatch { int n, B, C, S, Wx, Wd; const float* mixw; PoolBwdJob j[kMaxPool]; };
+
+static __global__ void __launch_bounds__(kThreads) k_pool_bwd(const __grid_constant__ PoolBwdBatch P) {
+  const PoolBwdJob& J = P.j[blockIdx.z];
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 8 + warp;
+  if (b >= P.B) return;
+  GNAS_DYN_SMEM(float, smem);
+  float* xrow = smem + warp * (P.Wx + 2 * P.Wd);
+  float* dm = xrow + P.Wx;     // dz of the max pool, index i <-> l = i - 4
+  float* da = dm + P.Wd;       // dz of the avg pool already divided by the window count
+  const int S = P.S;
+  const float* xg = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
+  const float* gg = J.g + (long long)b * J.gbs + (long long)c * J.Lo;
+  for (int p = lane; p < P.Wx; p += 32) {
+    const int pos = p - 2;
+    xrow[p] = (pos >= 0 && pos < J.Lin) ? xg[pos] : -INFINITY;
+  }
+  const long long zo = ((long long)b * P.C + c) * J.Lo;
+  for (int i = lane; i < P.Wd; i += 32) {
+    const int l = i - 4;
+    float vm = 0.f, va = 0.f;
+    if (l >= 0 && l < J.Lo) {
+      const float gv = gg[l];
+      if (J.zmax) vm = fmaf(J.coef_max[c], gv, fmaf(J.coef_max[P.C + c], J.zmax[zo + l], J.coef_max[2 * P.C + c]));
+      if (J.zavg) {
+        const int lo = max(l * S - 2, 0), hi = min(l * S + 2, J.Lin - 1);
+        va = fmaf(J.coef_avg[c], gv, fmaf(J.coef_avg[P.C + c], J.zavg[zo + l], J.coef_avg[2 * P.C + c])) / (float)(hi - lo + 1);
+      }
+    }
+    dm[i] = vm; da[i] = va;
+  }
+  __syncwarp();
+  const float wskip = J.skip_widx >= 0 ? P.mixw[J.skip_widx] : 0.f;
+  float* drow = J.dx + (long long)b * J.dxbs + (long long)c * J.Lin;
+  for (int m = lane; m < J.Lin; m += 32) {
+    float a = 0.f;
+    // windows l with l*S-2 <= m <= l*S+2
+    int l_lo = (m - 2 + S - 1) / S; if (m - 2 < 0) l_lo = 0;
+    int l_hi = (m + 2) / S; if (l_hi > J.Lo - 1) l_hi = J.Lo - 1;
+    for (int l = l_lo; l <= l_hi; ++l) {
+      a += da[l + 4];
+      if (J.zmax) {
+        // first maximal element of window l (torch max_pool1d backward routes there)
+        const float* wv = xrow + l * S;   // index 0 <-> pos l*S-2
+        int am = 0; float best = wv[0];
+#pragma unroll
+        for (int t = 1; t < 5; ++t) if (wv[t] > best) { best = wv[t]; am = t; }
+        if (l * S - 2 + am == m) a += dm[l + 4];
+      }
+    }
+    if (J.skip_widx >= 0) {
+      float gv = gg[m] * wskip;
+      if (J.skip_mask) gv *= J.skip_mask[((long long)b * P.C + c) * J.Lin + m];
+      a += gv;
+    }
+    drow[m] += a;
+  }
+}
+
+// ------------------------------------------------------------------ small helpers
+struct SliceCopy { const float* src; long long sbs; float* dst; long long dbs; int B, CL; };
+static __global__ void __launch_bounds__(kThreads) k_copy_rows(const __grid_constant__ SliceCopy P) {
+  const long long total = (long long)P.B * P.CL;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / P.CL);
+    const int r = (int)(i - (long long)b * P.CL);
+    P.dst[(long long)b * P.dbs + r] = P.src[(long long)b * P.sbs + r];
+  }
+}
+
+static __global__ void k_double_to_float(const double* src, float* dst, int n, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = accumulate ? dst[i] + (float)src[i] : (float)src[i];
+}
+
+}  // namespace gnas

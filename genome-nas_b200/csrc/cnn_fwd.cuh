@@ -1,0 +1,334 @@
+// Forward kernels of the MixedOp / CNN cell path (fp32, NCL layout).
+//
+// Reference arithmetic being replaced (all executed there by ATen/cuDNN calls):
+//   generalNAS_tools/operations_14_9.py:17-30,67-81,124-135,164-206,280-300
+//   darts_tools/model_discCNN.py:46-93 (MixedOp), :96-201 (CNN_Cell_search)
+// Every candidate ends in training-mode BatchNorm1d(affine=False), so an edge is
+// evaluated in phases: raw convolution outputs + per-channel (sum, sumsq) ->
+// finalize (mean, rstd) -> consumers normalise on load (stage 2) or in the mix.
+#pragma once
+#include "common.cuh"
+
+namespace gnas {
+
+// ------------------------------------------------------------------ weight packing
+struct PackJob { const float* src; float* dst; int Cout, Cin, KW, mode; };  // mode 0: [ci][t][co], 1: [co][t][ci]
+constexpr int kMaxPack = 160;
+struct PackBatch { int n; PackJob j[kMaxPack]; };
+
+static __global__ void __launch_bounds__(256) k_pack_weights(const __grid_constant__ PackBatch P) {
+  const PackJob& J = P.j[blockIdx.y];
+  const int total = J.Cout * J.Cin * J.KW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i % J.KW;
+    const int ci = (i / J.KW) % J.Cin;
+    const int co = i / (J.KW * J.Cin);
+    const int o = J.mode == 0 ? (ci * J.KW + t) * J.Cout + co : (co * J.KW + t) * J.Cin + ci;
+    J.dst[o] = J.src[i];
+  }
+}
+
+// ------------------------------------------------------------------ dense KW-tap conv
+struct DenseJob {
+  const float* x; long long xbs;   // input [B][Cin][Lin], batch stride in floats
+  const float* in_stat;            // mean[Cin] | rstd[Cin] (T_BN_RELU / T_BN) or null
+  const float* wp;                 // packed [Cin][KW][Cout]
+  float* z; long long zbs;         // raw output [B][Cout][Lout]
+  double* acc;                     // sum[Cout] | sumsq[Cout], or null
+  int Cin, Lin, Lout, tin;
+};
+constexpr int kMaxDense = 32;
+struct DenseBatch { int n, B, Cout, TL, pad, KC; DenseJob j[kMaxDense]; };
+
+template <int TM> struct WVec;
+template <> struct WVec<2> { static __device__ __forceinline__ void ld(const float* p, float* w) { float2 v = *reinterpret_cast<const float2*>(p); w[0] = v.x; w[1] = v.y; } };
+template <> struct WVec<4> { static __device__ __forceinline__ void ld(const float* p, float* w) { float4 v = *reinterpret_cast<const float4*>(p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; } };
+template <> struct WVec<8> { static __device__ __forceinline__ void ld(const float* p, float* w) { WVec<4>::ld(p, w); WVec<4>::ld(p + 4, w + 4); } };
+
+// z[b,co,l] = sum_{ci,t} W[co,ci,t] * T(x)[b,ci,l*S+t-pad]  (+ per-channel sum / sumsq of z)
+// CTA: one batch row, TL output positions, all Cout channels; thread tile TM x 4.
+template <int KW, int S, int TM>
+__global__ void __launch_bounds__(kThreads) k_dense_fwd(const __grid_constant__ DenseBatch P) {
+  const DenseJob& J = P.j[blockIdx.z];
+  const int TL = P.TL, l0 = blockIdx.x * TL;
+  if (l0 >= J.Lout) return;
+  const int b = blockIdx.y, Cout = P.Cout, KC = P.KC;
+  const int ncog = Cout / TM, nlg = TL / 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cog = tid / nlg, lg = tid - cog * nlg;
+  const bool active = cog < ncog;
+  constexpr int NX = 3 * S + KW;
+  constexpr int NX4 = (NX + 3) / 4;
+  const int Wu = (TL - 1) * S + KW;             // used width of an xs row
+  const int Wp = (Wu + 3) / 4 * 4 + 4;          // padded pitch (window over-read stays inside)
+  GNAS_DYN_SMEM(float, smem);
+  float* xs = smem;                             // [KC][Wp]
+  float* ws = xs + KC * Wp;                     // [KC][KW][Cout]
+  float* ssum = ws + KC * KW * Cout;            // [2][Cout]
+  for (int i = tid; i < 2 * Cout; i += kThreads) ssum[i] = 0.f;
+  float acc[TM][4];
+#pragma unroll
+  for (int m = 0; m < TM; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[m][n] = 0.f;
+  const int in0 = l0 * S - P.pad;
+  const float* xb = J.x + (long long)b * J.xbs;
+  for (int c0 = 0; c0 < J.Cin; c0 += KC) {
+    for (int ci = warp; ci < KC; ci += kThreads / 32) {
+      const float* xr = xb + (long long)(c0 + ci) * J.Lin;
+      float mean = 0.f, rstd = 1.f;
+      if (J.tin >= T_BN_RELU) { mean = J.in_stat[c0 + ci]; rstd = J.in_stat[J.Cin + c0 + ci]; }
+      for (int p = lane; p < Wp; p += 32) {
+        const int pos = in0 + p;
+        float v = 0.f;
+        if (p < Wu && pos >= 0 && pos < J.Lin) v = apply_tin(xr[pos], J.tin, mean, rstd);
+        xs[ci * Wp + p] = v;
+      }
+    }
+    {
+      const float4* src = reinterpret_cast<const float4*>(J.wp + (long long)c0 * KW * Cout);
+      float4* dst = reinterpret_cast<float4*>(ws);
+      const int n4 = KC * KW * Cout / 4;
+      for (int i = tid; i < n4; i += kThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (active) {
+      for (int ci = 0; ci < KC; ++ci) {
+        float xr[NX4 * 4];
+        const float4* xp = reinterpret_cast<const float4*>(xs + ci * Wp + lg * 4 * S);
+#pragma unroll
+        for (int q = 0; q < NX4; ++q) { float4 v = xp[q]; xr[4 * q] = v.x; xr[4 * q + 1] = v.y; xr[4 * q + 2] = v.z; xr[4 * q + 3] = v.w; }
+        const float* wrow = ws + ci * KW * Cout + cog * TM;
+#pragma unroll
+        for (int t = 0; t < KW; ++t) {
+          float w[TM];
+          WVec<TM>::ld(wrow + t * Cout, w);
+#pragma unroll
+          for (int m = 0; m < TM; ++m)
+#pragma unroll
+            for (int n = 0; n < 4; ++n) acc[m][n] = fmaf(w[m], xr[n * S + t], acc[m][n]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- epilogue: store raw z, accumulate statistics
+  const int lbase = l0 + 4 * lg;
+  float* zb = J.z + (long long)b * J.zbs;
+  const bool vec = active && (J.Lout % 4 == 0) && (J.zbs % 4 == 0) && (lbase + 3 < J.Lout);
+  const bool pow2 = (nlg & (nlg - 1)) == 0;
+  const int width = nlg < 32 ? nlg : 32;
+#pragma unroll
+  for (int m = 0; m < TM; ++m) {
+    const int co = cog * TM + m;
+    float s = 0.f, q = 0.f;
+    if (active) {
+      float* zr = zb + (long long)co * J.Lout;
+      if (vec) {
+        *reinterpret_cast<float4*>(zr + lbase) = make_float4(acc[m][0], acc[m][1], acc[m][2], acc[m][3]);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { s += acc[m][n]; q += acc[m][n] * acc[m][n]; }
+      } else {
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+          if (lbase + n < J.Lout) { zr[lbase + n] = acc[m][n]; s += acc[m][n]; q += acc[m][n] * acc[m][n]; }
+      }
+    }
+    if (J.acc != nullptr) {
+      if (pow2) {
+        for (int o = width >> 1; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+        if (active && (lg & (width - 1)) == 0) { atomicAdd(&ssum[co], s); atomicAdd(&ssum[Cout + co], q); }
+      } else if (active) {
+        atomicAdd(&ssum[co], s); atomicAdd(&ssum[Cout + co], q);
+      }
+    }
+  }
+  if (J.acc != nullptr) {
+    __syncthreads();
+    for (int i = tid; i < 2 * Cout; i += kThreads) atomicAdd(&J.acc[i], (double)ssum[i]);
+  }
+}
+
+// ------------------------------------------------------------------ depthwise conv
+struct DwJob {
+  const float* x; long long xbs;
+  const float* in_stat;            // mean | rstd of the producer BN (T_BN_RELU) or null
+  const float* wd;                 // [C][K]
+  float* u; long long ubs;         // output [B][C][Lout]
+  int Lin, Lout, tin;
+};
+constexpr int kMaxDw = 16;
+struct DwBatch { int n, B, C, pad, Wp; DwJob j[kMaxDw]; };
+
+// u[b,c,l] = sum_t wd[c,t] * T(x)[b,c,l*S+t*D-pad];  CTA: batch row b, 8 channels (one per warp)
+template <int K, int D, int S>
+__global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwBatch P) {
+  const DwJob& J = P.j[blockIdx.z];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 8 + warp;
+  constexpr int NX = 3 * S + (K - 1) * D + 1;
+  constexpr int NX4 = (NX + 3) / 4;
+  GNAS_DYN_SMEM(float, smem);
+  float* row = smem + warp * P.Wp;
+  if (c < P.C) {
+    const float* xr = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
+    float mean = 0.f, rstd = 1.f;
+    if (J.tin >= T_BN_RELU) { mean = J.in_stat[c]; rstd = J.in_stat[P.C + c]; }
+    for (int p = lane; p < P.Wp; p += 32) {
+      const int pos = p - P.pad;
+      row[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xr[pos], J.tin, mean, rstd) : 0.f;
+    }
+  }
+  __syncwarp();
+  if (c >= P.C) return;
+  float w[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) w[t] = J.wd[c * K + t];
+  float* ur = J.u + (long long)b * J.ubs + (long long)c * J.Lout;
+  const bool vecok = (J.Lout % 4 == 0) && (J.ubs % 4 == 0);
+  for (int g = lane; g * 4 < J.Lout; g += 32) {
+    float xw[NX4 * 4];
+    const float4* xp = reinterpret_cast<const float4*>(row + g * 4 * S);
+#pragma unroll
+    for (int q = 0; q < NX4; ++q) { float4 v = xp[q]; xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w; }
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < K; ++t)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) a[n] = fmaf(w[t], xw[n * S + t * D], a[n]);
+    if (vecok && g * 4 + 3 < J.Lout) *reinterpret_cast<float4*>(ur + g * 4) = make_float4(a[0], a[1], a[2], a[3]);
+    else
+      for (int n = 0; n < 4; ++n) if (g * 4 + n < J.Lout) ur[g * 4 + n] = a[n];
+  }
+}
+
+// ------------------------------------------------------------------ pools
+struct PoolJob {
+  const float* x; long long xbs;
+  float* zmax; float* zavg;          // [B][C][Lout] contiguous, either may be null
+  double* acc_max; double* acc_avg;  // sum | sumsq
+  int Lin, Lout;
+};
+constexpr int kMaxPool = 8;
+struct PoolBatch { int n, B, C, S; PoolJob j[kMaxPool]; };
+
+// MaxPool1d(5,pad 2, -inf padding) and AvgPool1d(5,pad 2,count_include_pad=False) in one pass over x.
+// CTA: channel c (blockIdx.x), 8 batch rows (one per warp).
+static __global__ void __launch_bounds__(kThreads) k_pool_fwd(const __grid_constant__ PoolBatch P) {
+  const PoolJob& J = P.j[blockIdx.z];
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 8 + warp;
+  __shared__ float red[4][8];
+  float sm = 0.f, qm = 0.f, sa = 0.f, qa = 0.f;
+  if (b < P.B) {
+    const float* xr = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
+    const long long o = ((long long)b * P.C + c) * J.Lout;
+    for (int l = lane; l < J.Lout; l += 32) {
+      const int s0 = l * P.S - 2;
+      float mx = -INFINITY, sum = 0.f;
+      int cnt = 0;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {
+        const int pos = s0 + t;
+        if (pos >= 0 && pos < J.Lin) { const float v = xr[pos]; mx = v > mx ? v : mx; sum += v; ++cnt; }
+      }
+      if (J.zmax) { J.zmax[o + l] = mx; sm += mx; qm += mx * mx; }
+      if (J.zavg) { const float a = sum / (float)cnt; J.zavg[o + l] = a; sa += a; qa += a * a; }
+    }
+  }
+  sm = warp_sum(sm); qm = warp_sum(qm); sa = warp_sum(sa); qa = warp_sum(qa);
+  if (lane == 0) { red[0][warp] = sm; red[1][warp] = qm; red[2][warp] = sa; red[3][warp] = qa; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += (double)red[threadIdx.x][w];
+    double* dst = threadIdx.x < 2 ? J.acc_max : J.acc_avg;
+    if (dst) atomicAdd(&dst[(threadIdx.x & 1) * P.C + c], t);
+  }
+}
+
+// ------------------------------------------------------------------ BN finalize
+constexpr int kMaxSlots = 288;
+struct FinBatch {
+  double* acc;          // [slot][2][C]
+  float* stat;          // [slot][2][C]  (mean | rstd)
+  float* running;       // flat running-stat buffer (mean at off, var at off + C) or null
+  int C, nslots, training;
+  float momentum;
+  short slot[kMaxSlots];
+  float count[kMaxSlots];
+  long long rs_off[kMaxSlots];
+};
+
+static __global__ void k_bn_finalize(const __grid_constant__ FinBatch P) {
+  const int s = P.slot[blockIdx.x];
+  const double n = (double)P.count[blockIdx.x];
+  for (int c = threadIdx.x; c < P.C; c += blockDim.x) {
+    const long long ro = P.rs_off[blockIdx.x];
+    float* st = P.stat + (long long)s * 2 * P.C;
+    if (P.training) {
+      const double* a = P.acc + (long long)s * 2 * P.C;
+      const double mean = a[c] / n;
+      double var = a[P.C + c] / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      st[c] = (float)mean;
+      st[P.C + c] = (float)(1.0 / sqrt(var + (double)kBnEps));
+      if (P.running != nullptr && ro >= 0) {
+        float* rm = P.running + ro;
+        const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+        rm[c] = (1.f - P.momentum) * rm[c] + P.momentum * (float)mean;
+        rm[P.C + c] = (1.f - P.momentum) * rm[P.C + c] + P.momentum * (float)unb;
+      }
+    } else {
+      const float* rm = P.running + ro;
+      st[c] = rm[c];
+      st[P.C + c] = 1.0f / sqrtf(rm[P.C + c] + kBnEps);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ y = BN(z) [* gamma + beta]
+struct BnApplyJob { const float* z; float* y; const float* stat; const float* gamma; const float* beta; int C, L; long long total; };
+struct BnApplyBatch { int n; BnApplyJob j[4]; };
+
+static __global__ void __launch_bounds__(kThreads) k_bn_apply(const __grid_constant__ BnApplyBatch P) {
+  const BnApplyJob& J = P.j[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < J.total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / J.L) % J.C);
+    float v = (J.z[i] - J.stat[c]) * J.stat[J.C + c];
+    if (J.gamma) v = v * J.gamma[c] + J.beta[c];
+    J.y[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ alpha-weighted mix of one node
+struct MixTerm {
+  const float* z; long long bs;  // tensor [B][C][L] with batch stride
+  const float* stat;             // mean | rstd, or null for the stride-1 skip (plain x)
+  const float* mask;             // skip-connect dropout mask (pre-scaled) or null
+  int widx;                      // index into the mixing-weight matrix
+};
+constexpr int kMaxTerms = 40;
+struct MixBatch { int B, C, L, nterms; float* out; long long obs; const float* mixw; MixTerm t[kMaxTerms]; };
+
+// node[b,c,l] = sum_terms w * (z - mean[c]) * rstd[c]      (model_discCNN.py:93,195)
+static __global__ void __launch_bounds__(kThreads) k_mix_fwd(const __grid_constant__ MixBatch P) {
+  const long long total = (long long)P.B * P.C * P.L;
+  const int CL = P.C * P.L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / CL);
+    const int r = (int)(i - (long long)b * CL);
+    const int c = r / P.L;
+    float a = 0.f;
+    for (int t = 0; t < P.nterms; ++t) {
+      const MixTerm& T = P.t[t];
+      float v = T.z[(long long)b * T.bs + r];
+      if (T.stat) v = (v - T.stat[c]) * T.stat[P.C + c];
+      else if (T.mask) v *= T.mask[i];
+      a = fmaf(P.mixw[T.widx], v, a);
+    }
+    P.out[(long long)b * P.obs + r] = a;
+  }
+}
+
+}  // namespace gnas

@@ -1,0 +1,69 @@
+// Shared device/host helpers for the genomeDARTS sm_100a kernels.
+#pragma once
+#ifdef GNAS_EMUL
+// tests/emul/cuda_emul.h is force-included by the emulator build (test infrastructure only)
+#define GNAS_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  emul::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); }, false)
+#define GNAS_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
+  emul::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); }, true)
+#define GNAS_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emul::cur_block()->dyn_smem)
+#define GNAS_SET_SMEM(kernel, bytes) 0
+#define GNAS_SPIN_PAUSE() GNAS_EMUL_YIELD()
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#define GNAS_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define GNAS_DYN_SMEM(T, name)                                       \
+  extern __shared__ __align__(16) unsigned char gnas_dyn_smem_raw[]; \
+  T* name = reinterpret_cast<T*>(gnas_dyn_smem_raw)
+#define GNAS_SET_SMEM(kernel, bytes) \
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#define GNAS_SPIN_PAUSE() __nanosleep(32)
+#endif
+
+#define GNAS_OK 0
+#define GNAS_ERR_ARG (-1)
+#define GNAS_ERR_SHAPE (-2)
+#define GNAS_ERR_UNSUPPORTED (-3)
+#define GNAS_ERR_WORKSPACE (-4)
+
+namespace gnas {
+
+constexpr int kThreads = 256;
+constexpr float kBnEps = 1e-5f;
+
+// how a tensor is transformed while it is read
+enum : int { T_NONE = 0, T_RELU = 1, T_BN_RELU = 2, T_BN = 3 };
+// where the result of a backward data kernel goes
+enum : int { O_STORE = 0, O_RELU_ACC = 1, O_BNRELU_STORE = 2, O_ACC = 3 };
+
+void set_error(const char* msg);
+int check_launch(const char* what);
+
+__device__ __forceinline__ float apply_tin(float v, int tin, float mean, float rstd) {
+  if (tin == T_RELU) return v > 0.f ? v : 0.f;
+  if (tin == T_BN_RELU) { v = (v - mean) * rstd; return v > 0.f ? v : 0.f; }
+  if (tin == T_BN) return (v - mean) * rstd;
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return cdiv(a, b) * b; }
+
+}  // namespace gnas

@@ -1,0 +1,282 @@
+// Host-side launch helpers: pick tile shapes, size shared memory, dispatch the
+// template instance.  One process per GPU; everything is enqueued on the
+// caller's stream and nothing here synchronises.
+#pragma once
+#include "cnn_fwd.cuh"
+#include "cnn_bwd.cuh"
+
+namespace gnas {
+
+#ifdef GNAS_EMUL
+#define GNAS_PREP_SMEM(kernel, bytes) do { } while (0)
+#else
+#define GNAS_PREP_SMEM(kernel, bytes)                                                       \
+  do {                                                                                      \
+    static int prepared_bytes = 0;                                                          \
+    if ((int)(bytes) > prepared_bytes) {                                                    \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+      prepared_bytes = (int)(bytes);                                                        \
+    }                                                                                       \
+  } while (0)
+#endif
+
+static inline int choose_tm(int C) {
+  if (C % 8 == 0 && C >= 32) return 8;
+  if (C % 4 == 0 && C >= 16) return 4;
+  return 2;
+}
+static inline int choose_kc(int kw, const int* cins, int n) {
+  int kc = kw == 1 ? 16 : 8;
+  for (;;) {
+    bool ok = true;
+    for (int i = 0; i < n; ++i) ok = ok && (cins[i] % kc == 0);
+    if (ok || kc == 1) return kc;
+    kc >>= 1;
+  }
+}
+
+// ------------------------------------------------------------------ dense forward
+template <int KW, int S, int TM>
+static void launch_dense_fwd_t(DenseBatch& b, int maxLout, cudaStream_t st) {
+  const int ncog = b.Cout / TM;
+  const int nlg = kThreads / ncog;
+  b.TL = 4 * nlg;
+  const int Wp = ((b.TL - 1) * S + KW + 3) / 4 * 4 + 4;
+  const size_t smem = sizeof(float) * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cout + 2 * b.Cout);
+  GNAS_PREP_SMEM((k_dense_fwd<KW, S, TM>), smem);
+  dim3 grid(cdiv(maxLout, b.TL), b.B, b.n);
+  GNAS_LAUNCH((k_dense_fwd<KW, S, TM>), grid, dim3(kThreads), smem, st, b);
+}
+template <int KW, int S>
+static void launch_dense_fwd_s(DenseBatch& b, int maxLout, cudaStream_t st) {
+  switch (choose_tm(b.Cout)) {
+    case 8: launch_dense_fwd_t<KW, S, 8>(b, maxLout, st); break;
+    case 4: launch_dense_fwd_t<KW, S, 4>(b, maxLout, st); break;
+    default: launch_dense_fwd_t<KW, S, 2>(b, maxLout, st); break;
+  }
+}
+// KW in {1, 13, 15}, S in {1, 2, 3}
+static int launch_dense_fwd(int KW, int S, DenseBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  int cins[kMaxDense], maxL = 0;
+  for (int i = 0; i < b.n; ++i) { cins[i] = b.j[i].Cin; maxL = b.j[i].Lout > maxL ? b.j[i].Lout : maxL; }
+  b.KC = choose_kc(KW, cins, b.n);
+  if (KW == 15 && S == 1) launch_dense_fwd_s<15, 1>(b, maxL, st);
+  else if (KW == 15 && S == 2) launch_dense_fwd_s<15, 2>(b, maxL, st);
+  else if (KW == 15 && S == 3) launch_dense_fwd_s<15, 3>(b, maxL, st);
+  else if (KW == 1 && S == 1) launch_dense_fwd_s<1, 1>(b, maxL, st);
+  else if (KW == 1 && S == 2) launch_dense_fwd_s<1, 2>(b, maxL, st);
+  else if (KW == 1 && S == 3) launch_dense_fwd_s<1, 3>(b, maxL, st);
+  else if (KW == 13 && S == 1) launch_dense_fwd_s<13, 1>(b, maxL, st);
+  else { set_error("dense_fwd: unsupported (KW, stride)"); return GNAS_ERR_UNSUPPORTED; }
+  b.n = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------ depthwise forward
+template <int K, int D, int S>
+static void launch_dw_fwd_t(DwBatch& b, cudaStream_t st) {
+  constexpr int NX = 3 * S + (K - 1) * D + 1;
+  constexpr int NX4 = (NX + 3) / 4;
+  int wp = 0;
+  for (int i = 0; i < b.n; ++i) {
+    const int g4 = cdiv(b.j[i].Lout, 4);
+    int need = (g4 - 1) * 4 * S + NX4 * 4;
+    const int need2 = b.pad + b.j[i].Lin;
+    need = need > need2 ? need : need2;
+    wp = need > wp ? need : wp;
+  }
+  b.Wp = round_up(wp, 4) + 4;
+  const size_t smem = sizeof(float) * 8 * (size_t)b.Wp;
+  GNAS_PREP_SMEM((k_dw_fwd<K, D, S>), smem);
+  dim3 grid(cdiv(b.C, 8), b.B, b.n);
+  GNAS_LAUNCH((k_dw_fwd<K, D, S>), grid, dim3(kThreads), smem, st, b);
+}
+static int launch_dw_fwd(int K, int D, int S, DwBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+#define GNAS_DW_CASE(k, d, s) if (K == k && D == d && S == s) launch_dw_fwd_t<k, d, s>(b, st); else
+  GNAS_DW_CASE(15, 1, 1) GNAS_DW_CASE(15, 1, 2) GNAS_DW_CASE(15, 1, 3)
+  GNAS_DW_CASE(9, 1, 1) GNAS_DW_CASE(9, 1, 2) GNAS_DW_CASE(9, 1, 3)
+  GNAS_DW_CASE(15, 2, 1) GNAS_DW_CASE(15, 2, 2) GNAS_DW_CASE(15, 2, 3)
+  GNAS_DW_CASE(9, 2, 1) GNAS_DW_CASE(9, 2, 2) GNAS_DW_CASE(9, 2, 3)
+  { set_error("dw_fwd: unsupported (K, D, S)"); return GNAS_ERR_UNSUPPORTED; }
+#undef GNAS_DW_CASE
+  b.n = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------ transposed dense (dx)
+template <int KW, int S, int TM>
+static void launch_dense_dx_t(DxBatch& b, int maxLin, cudaStream_t st) {
+  const int ncig = b.Cin / TM;
+  b.nq = kThreads / (ncig * S);
+  constexpr int NT = (KW + S - 1) / S;
+  const int Wu = 4 * b.nq + NT + 1;
+  const int Wp = (Wu + 3) / 4 * 4 + 4;
+  const size_t smem = sizeof(float) * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cin + 2 * b.Cin);
+  GNAS_PREP_SMEM((k_dense_bwd_dx<KW, S, TM>), smem);
+  dim3 grid(cdiv(maxLin, 4 * S * b.nq), b.B, b.n);
+  GNAS_LAUNCH((k_dense_bwd_dx<KW, S, TM>), grid, dim3(kThreads), smem, st, b);
+}
+template <int KW, int S>
+static void launch_dense_dx_s(DxBatch& b, int maxLin, cudaStream_t st) {
+  switch (choose_tm(b.Cin)) {
+    case 8: launch_dense_dx_t<KW, S, 8>(b, maxLin, st); break;
+    case 4: launch_dense_dx_t<KW, S, 4>(b, maxLin, st); break;
+    default: launch_dense_dx_t<KW, S, 2>(b, maxLin, st); break;
+  }
+}
+static int launch_dense_dx(int KW, int S, DxBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  int couts[kMaxDense], maxL = 0;
+  for (int i = 0; i < b.n; ++i) { couts[i] = b.j[i].Cout; maxL = b.j[i].Lin > maxL ? b.j[i].Lin : maxL; }
+  b.KC = choose_kc(KW, couts, b.n);
+  if (KW == 15 && S == 1) launch_dense_dx_s<15, 1>(b, maxL, st);
+  else if (KW == 15 && S == 2) launch_dense_dx_s<15, 2>(b, maxL, st);
+  else if (KW == 15 && S == 3) launch_dense_dx_s<15, 3>(b, maxL, st);
+  else if (KW == 1 && S == 1) launch_dense_dx_s<1, 1>(b, maxL, st);
+  else if (KW == 1 && S == 2) launch_dense_dx_s<1, 2>(b, maxL, st);
+  else if (KW == 1 && S == 3) launch_dense_dx_s<1, 3>(b, maxL, st);
+  else { set_error("dense_dx: unsupported (KW, stride)"); return GNAS_ERR_UNSUPPORTED; }
+  b.n = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------ weight gradients
+static inline int pick_tc(int a, int b) {
+  const int m = a < b ? a : b;
+  if (a % 8 == 0 && b % 8 == 0 && m >= 64) return 8;
+  if (a % 4 == 0 && b % 4 == 0 && m >= 16) return 4;
+  if (a % 2 == 0 && b % 2 == 0 && m >= 8) return 2;
+  return 1;
+}
+template <int TC>
+static void launch_pw_wgrad_t(WgBatch& b, int maxblocks, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (size_t)b.TL * (b.COB + 4 + b.CIB + 4);
+  GNAS_PREP_SMEM((k_pw_wgrad<TC>), smem);
+  dim3 grid(maxblocks, cdiv(b.B, b.BCH), b.n);
+  GNAS_LAUNCH((k_pw_wgrad<TC>), grid, dim3(kThreads), smem, st, b);
+}
+// all jobs of a batch must share Cin (true for every call site)
+static int launch_pw_wgrad(int S, WgBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  const int Cin = b.j[0].Cin;
+  for (int i = 1; i < b.n; ++i) if (b.j[i].Cin != Cin) { set_error("pw_wgrad: mixed Cin"); return GNAS_ERR_ARG; }
+  const int TC = pick_tc(b.Cout, Cin);
+  b.S = S; b.pad = 0;
+  b.COB = b.Cout < 16 * TC ? b.Cout : 16 * TC;
+  b.CIB = Cin < 16 * TC ? Cin : 16 * TC;
+  while ((b.COB / TC) * (b.CIB / TC) > kThreads) b.CIB /= 2;
+  b.TL = 64;
+  b.BCH = b.B >= 32 ? 8 : (b.B >= 8 ? 4 : 1);
+  const int nblk = cdiv(b.Cout, b.COB) * cdiv(Cin, b.CIB);
+  if (b.Cout % b.COB || Cin % b.CIB) { set_error("pw_wgrad: channel counts must tile"); return GNAS_ERR_SHAPE; }
+  switch (TC) {
+    case 8: launch_pw_wgrad_t<8>(b, nblk, st); break;
+    case 4: launch_pw_wgrad_t<4>(b, nblk, st); break;
+    case 2: launch_pw_wgrad_t<2>(b, nblk, st); break;
+    default: launch_pw_wgrad_t<1>(b, nblk, st); break;
+  }
+  b.n = 0;
+  return 0;
+}
+
+template <int KW, int S>
+static void launch_conv_wgrad_t(WgBatch& b, int nblk, cudaStream_t st) {
+  const int per = (b.COB / 4) * b.CIB;
+  const int G = kThreads / per;
+  int tlg = 512 / G;
+  tlg = tlg > 64 ? 64 : (tlg < 16 ? 16 : tlg);
+  b.TL = tlg;
+  const int TLc = tlg * G;
+  const int pz = TLc | 1, pr = ((TLc - 1) * S + KW) | 1;
+  const size_t smem = sizeof(float) * ((size_t)b.COB * pz + (size_t)b.CIB * pr);
+  GNAS_PREP_SMEM((k_conv_wgrad<KW, S>), smem);
+  dim3 grid(nblk, cdiv(b.B, b.BCH), b.n);
+  GNAS_LAUNCH((k_conv_wgrad<KW, S>), grid, dim3(kThreads), smem, st, b);
+}
+static int launch_conv_wgrad(int KW, int S, int pad, WgBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  const int Cin = b.j[0].Cin;
+  for (int i = 1; i < b.n; ++i) if (b.j[i].Cin != Cin) { set_error("conv_wgrad: mixed Cin"); return GNAS_ERR_ARG; }
+  b.S = S; b.pad = pad;
+  b.COB = b.Cout < 32 ? b.Cout : 32;
+  b.CIB = Cin < 32 ? Cin : 32;
+  if (b.Cout % b.COB || Cin % b.CIB || b.COB % 4) { set_error("conv_wgrad: channel counts must tile"); return GNAS_ERR_SHAPE; }
+  b.BCH = b.B >= 32 ? 8 : (b.B >= 8 ? 4 : 1);
+  const int nblk = (b.Cout / b.COB) * (Cin / b.CIB);
+  if (KW == 15 && S == 1) launch_conv_wgrad_t<15, 1>(b, nblk, st);
+  else if (KW == 15 && S == 2) launch_conv_wgrad_t<15, 2>(b, nblk, st);
+  else if (KW == 15 && S == 3) launch_conv_wgrad_t<15, 3>(b, nblk, st);
+  else if (KW == 13 && S == 1) launch_conv_wgrad_t<13, 1>(b, nblk, st);
+  else { set_error("conv_wgrad: unsupported (KW, stride)"); return GNAS_ERR_UNSUPPORTED; }
+  b.n = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------ depthwise backward
+template <int K, int D, int S>
+static void launch_dw_bwd_t(DwBwdBatch& b, cudaStream_t st) {
+  int wx = 0, wd = 0;
+  for (int i = 0; i < b.n; ++i) {
+    int a = b.j[i].Lin + 2 * b.pad;
+    const int a2 = (b.j[i].Lo - 1) * S + (K - 1) * D + 1;
+    a = a > a2 ? a : a2;
+    wx = a > wx ? a : wx;
+    const int d = (b.j[i].Lin + b.pad) / S + K + 2;
+    const int d2 = b.j[i].Lo + K + 2;
+    wd = d > wd ? d : wd;
+    wd = d2 > wd ? d2 : wd;
+  }
+  b.Wx = wx + 1; b.Wd = wd;
+  const size_t smem = sizeof(float) * 8 * (size_t)(b.Wx + b.Wd);
+  GNAS_PREP_SMEM((k_dw_bwd<K, D, S>), smem);
+  dim3 grid(b.C, cdiv(b.B, 8), b.n);
+  GNAS_LAUNCH((k_dw_bwd<K, D, S>), grid, dim3(kThreads), smem, st, b);
+}
+static int launch_dw_bwd(int K, int D, int S, DwBwdBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+#define GNAS_DW_CASE(k, d, s) if (K == k && D == d && S == s) launch_dw_bwd_t<k, d, s>(b, st); else
+  GNAS_DW_CASE(15, 1, 1) GNAS_DW_CASE(15, 1, 2) GNAS_DW_CASE(15, 1, 3)
+  GNAS_DW_CASE(9, 1, 1) GNAS_DW_CASE(9, 1, 2) GNAS_DW_CASE(9, 1, 3)
+  GNAS_DW_CASE(15, 2, 1) GNAS_DW_CASE(15, 2, 2) GNAS_DW_CASE(15, 2, 3)
+  GNAS_DW_CASE(9, 2, 1) GNAS_DW_CASE(9, 2, 2) GNAS_DW_CASE(9, 2, 3)
+  { set_error("dw_bwd: unsupported (K, D, S)"); return GNAS_ERR_UNSUPPORTED; }
+#undef GNAS_DW_CASE
+  b.n = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------ pools
+static int launch_pool_fwd(PoolBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  dim3 grid(b.C, cdiv(b.B, 8), b.n);
+  GNAS_LAUNCH(k_pool_fwd, grid, dim3(kThreads), 0, st, b);
+  b.n = 0;
+  return 0;
+}
+static int launch_pool_bwd(PoolBwdBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  int wx = 0, wd = 0;
+  for (int i = 0; i < b.n; ++i) {
+    int a = b.j[i].Lin + 4;
+    const int a2 = (b.j[i].Lo - 1) * b.S + 5;
+    a = a > a2 ? a : a2;
+    wx = a > wx ? a : wx;
+    wd = b.j[i].Lo + 8 > wd ? b.j[i].Lo + 8 : wd;
+  }
+  b.Wx = wx; b.Wd = wd;
+  const size_t smem = sizeof(float) * 8 * (size_t)(b.Wx + 2 * b.Wd);
+  GNAS_PREP_SMEM(k_pool_bwd, smem);
+  dim3 grid(b.C, cdiv(b.B, 8), b.n);
+  GNAS_LAUNCH(k_pool_bwd, grid, dim3(kThreads), smem, st, b);
+  b.n = 0;
+  return 0;
+}
+
+static inline int ew_blocks(long long total) {
+  long long nb = cdivll(total, kThreads);
+  return (int)(nb < 1 ? 1 : (nb > 148 * 16 ? 148 * 16 : nb));
+}
+
+}  // namespace gnas

@@ -164,7 +164,7 @@ static inline int atomicMax(int* a, int v) {
 }
 static inline unsigned emul_ld_acquire(const unsigned* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 
-static inline float __expf(float x) { return expf(x); }
+#define __expf(x) expf(x)
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
