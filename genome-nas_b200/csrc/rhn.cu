@@ -1,7 +1,821 @@
-// placeholder until the RHN kernels land
+// Recurrent highway layer of the search cell (DARTSCell.forward + DARTSCellSearch.cell).
+// Replaces darts_tools/model_discCNN.py:226-268 and model_search.py:54-97 behind include/gnas.h.
+//
+// Forward: ONE persistent cooperative kernel.  CTA c owns hidden columns [4c, 4c+4): its slices of
+// W0 (2H x 8) and of all eight Ws[i] (H x 8 each) stay in shared memory for the whole sequence
+// (H = 512: 160 KB).  BatchNorm over the batch is per column, hence CTA-local; each new state is
+// published (masked) to a ring in global memory and a grid barrier separates the 9 stages of a time
+// step.  When s_j appears it is multiplied at once with the slices of Ws[j..7] ("multiply on
+// arrival"): same FLOPs as the reference's per-step re-multiplication of all states, no concat.
+// All internal state is feature-major ([H][B]) so that a CTA's columns are contiguous rows.
+//
+// Backward: staged launches per (time step, node) -- elementwise/BN kernel + split-K GEMM against
+// Ws[i]^T -- and, off the critical path, one batched GEMM pass for dW0 / dWs over all time steps.
 #include "common.cuh"
 #include "../../include/gnas.h"
+
+namespace gnas {
+
+constexpr int kNC = 4;        // hidden columns per CTA in the persistent forward kernel
+constexpr int kKCH = 32;      // K rows per shared-memory chunk
+constexpr int kMaxBP = 64;    // padded batch rows supported by the persistent kernel
+
+#ifdef GNAS_EMUL
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait() {}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) { return emul_ld_acquire(p); }
+__device__ __forceinline__ int ld_volatile_i32(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ float ld_cg(const float* p) { return *p; }
+__device__ __forceinline__ long long gnas_clock() { return 0; }
+#else
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ long long gnas_clock() { return clock64(); }
+#endif
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// activation k in {0: tanh, 1: identity, 2: sigmoid, 3: relu}  (PRIMITIVES_rnn[1:], genotypes.py:42-48)
+__device__ __forceinline__ float act_f(int k, float h) {
+  switch (k) { case 0: return tanhf(h); case 1: return h; case 2: return sigmoidf_(h); default: return h > 0.f ? h : 0.f; }
+}
+__device__ __forceinline__ float act_df(int k, float h) {
+  switch (k) {
+    case 0: { const float t = tanhf(h); return 1.f - t * t; }
+    case 1: return 1.f;
+    case 2: { const float s = sigmoidf_(h); return s * (1.f - s); }
+    default: return h > 0.f ? 1.f : 0.f;
+  }
+}
+
+struct RhnTable {             // per edge p = i(i+1)/2 + j: index into probs for each activation, -1 if disabled
+  short pidx[GNAS_RNN_EDGES][4];
+};
+
+struct RhnPlan {
+  int BP;
+  long long xmT, xkT, hmT, h0T, ring, ST, CHT, C0T, HT, stat, bar, fwd_total;   // forward workspace (floats)
+  long long dsT, dhT, dxT, doT, dpacc, bwd_total;                              // backward scratch
+};
+
+static RhnPlan rhn_plan(const GnasRhnDesc* d) {
+  RhnPlan p;
+  const long long T = d->T, H = d->H;
+  p.BP = (d->B + 3) / 4 * 4;
+  const long long HB = H * p.BP;
+  long long o = 0;
+  p.xmT = o; o += T * HB;          // (x * x_mask)^T
+  p.xkT = o; o += HB;              // x_mask^T
+  p.hmT = o; o += HB;              // h_mask^T
+  p.h0T = o; o += HB;
+  p.ring = o; o += 10 * HB;        // masked s_0..s_8, masked h
+  p.ST = o; o += T * 9 * HB;       // unmasked states
+  p.CHT = o; o += T * 36 * 2 * HB; // pre-activations c|h per edge (overwritten by dc|dh in backward)
+  p.C0T = o; o += T * 2 * HB;
+  p.HT = o; o += T * HB;           // h_t^T
+  p.stat = o; o += T * 9 * 2 * H;
+  p.bar = o; o += 64;              // barrier counter + abort flag
+  p.fwd_total = o;
+  o = 0;
+  p.dpacc = o; o += 2 * 36 * 4;    // doubles
+  p.dsT = o; o += 9 * HB;
+  p.dhT = o; o += 2 * HB;          // ping-pong
+  p.dxT = o; o += T * HB;
+  p.bwd_total = o;
+  return p;
+}
+
+static void rhn_table(const GnasRhnDesc* d, RhnTable& tb) {
+  // comp_aux.py:127-233: probability row = edge index - #fully disabled edges so far; column = #enabled before k
+  int disc = 0;
+  for (int r = 0; r < GNAS_RNN_EDGES; ++r) {
+    bool any = false;
+    for (int k = 0; k < GNAS_RNN_PRIMS; ++k) any = any || d->sw[r][k];
+    if (!any) ++disc;
+    for (int k = 1; k < GNAS_RNN_PRIMS; ++k) {
+      int col = 0;
+      for (int q = 0; q < k; ++q) col += d->sw[r][q] ? 1 : 0;
+      tb.pidx[r][k - 1] = d->sw[r][k] ? (short)((r - disc) * d->n_prims + col) : (short)-1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ prologue / epilogue transposes
+struct RhnPro {
+  int T, B, BP, H;
+  const float* x; const float* h0; const float* xm; const float* hm;
+  float* xmT; float* xkT; float* hmT; float* h0T; float* ring9;
+};
+static __global__ void __launch_bounds__(256) k_rhn_prologue(const __grid_constant__ RhnPro P) {
+  const long long HB = (long long)P.H * P.BP;
+  const long long total = (long long)(P.T + 3) * HB;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int slab = (int)(i / HB);
+    const int r = (int)(i - (long long)slab * HB);
+    const int n = r / P.BP, m = r - n * P.BP;
+    const bool real = m < P.B;
+    const float xk = real ? (P.xm ? P.xm[m * P.H + n] : 1.f) : 0.f;
+    const float hk = real ? (P.hm ? P.hm[m * P.H + n] : 1.f) : 0.f;
+    if (slab < P.T) P.xmT[i] = real ? P.x[((long long)slab * P.B + m) * P.H + n] * xk : 0.f;
+    else if (slab == P.T) P.xkT[r] = xk;
+    else if (slab == P.T + 1) P.hmT[r] = hk;
+    else {
+      const float h = real ? P.h0[m * P.H + n] : 0.f;
+      P.h0T[r] = h;
+      P.ring9[r] = h * hk;
+    }
+  }
+}
+
+// dst[t][m][n] = src[t][n][m]   ([H][BP] -> [B][H])
+static __global__ void __launch_bounds__(256) k_rhn_untranspose(const float* src, float* dst, int T, int B, int BP, int H) {
+  const long long total = (long long)T * B * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % H);
+    const int m = (int)((i / H) % B);
+    const long long t = i / ((long long)H * B);
+    dst[i] = src[(t * H + n) * BP + m];
+  }
+}
+
+// ------------------------------------------------------------------ persistent forward kernel
+struct RhnFwd {
+  int T, B, BP, H, training;
+  float momentum;
+  const float* xmT; const float* hmT; const float* h0T;
+  const float* W0; const float* Ws; const float* probs;
+  float* ring; float* ST; float* CHT; float* C0T; float* HT; float* stat;
+  float* out; float* running;
+  unsigned* bar; int* abort_flag;
+  RhnTable tb;
+};
+
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, int* abort_flag, unsigned target, int* s_abort) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const long long t0 = gnas_clock();
+    int ab = 0;
+    while (ld_acquire_u32(bar) < target) {
+      GNAS_SPIN_PAUSE();
+      if (ld_volatile_i32(abort_flag)) { ab = 1; break; }
+      if (gnas_clock() - t0 > 4000000000LL) { atomicAdd(abort_flag, 1); ab = 1; break; }   // ~2 s: never hang the GPU
+    }
+    __threadfence();
+    *s_abort = ab;
+  }
+  __syncthreads();
+  return *s_abort != 0;
+}
+
+// K-split factor: power of two, fills the CTA, and keeps KS * N <= 64 columns of the partial buffer
+__device__ __forceinline__ int rhn_ks(int BP, int N) {
+  int a = kThreads / ((BP / 4) * (N / 4));
+  const int b = 64 / N;
+  a = a < b ? a : b;
+  return a >= 8 ? 8 : (a >= 4 ? 4 : (a >= 2 ? 2 : 1));
+}
+
+// C[m][n] partial = sum_k A[k][m] * W[k][n]; A streamed from global ([K][BP], already masked) in kKCH-row chunks
+// with cp.async double buffering; W slices resident in shared memory.  Result (K-split partials) -> part.
+__device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const float* __restrict__ A1, int K0, int K,
+                                         int BP, int N, const float* wbase, int wstride_i, int H_w, bool stage0,
+                                         float* abuf, float* part) {
+  const int tid = threadIdx.x;
+  const int nrg = BP / 4, ncg = N / 4;
+  const int KS = rhn_ks(BP, N);
+  const int rg = tid % nrg, cg = (tid / nrg) % ncg, ks = tid / (nrg * ncg);
+  const bool active = ks < KS;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  // W column group: stage 0 -> W0s[k][8]; stage j -> Wss[i][k][8] with i = cg / 2
+  const float* wcol = stage0 ? wbase + cg * 4 : wbase + (size_t)(cg >> 1) * wstride_i + (cg & 1) * 4;
+  (void)H_w;
+  const int nch = K / kKCH;
+  const int f4_per_chunk = kKCH * BP / 4;
+  auto issue = [&](int c) {
+    float* dst = abuf + (c & 1) * kKCH * BP;
+    const int k0 = c * kKCH;
+    const float* src = (k0 < K0) ? A0 + (size_t)k0 * BP : A1 + (size_t)(k0 - K0) * BP;
+    for (int i = tid; i < f4_per_chunk; i += kThreads) cp_async16(dst + 4 * i, src + 4 * i);
+    cp_async_commit();
+  };
+  issue(0);
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    if (active) {
+      const float* as = abuf + (c & 1) * kKCH * BP + rg * 4;
+      const float* wk = wcol + (size_t)(c * kKCH) * 8;
+#pragma unroll 4
+      for (int k = ks; k < kKCH; k += KS) {
+        const float4 a = *reinterpret_cast<const float4*>(as + k * BP);
+        const float4 w = *reinterpret_cast<const float4*>(wk + k * 8);
+        acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]); acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
+        acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]); acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
+        acc[2][0] = fmaf(a.z, w.x, acc[2][0]); acc[2][1] = fmaf(a.z, w.y, acc[2][1]); acc[2][2] = fmaf(a.z, w.z, acc[2][2]); acc[2][3] = fmaf(a.z, w.w, acc[2][3]);
+        acc[3][0] = fmaf(a.w, w.x, acc[3][0]); acc[3][1] = fmaf(a.w, w.y, acc[3][1]); acc[3][2] = fmaf(a.w, w.z, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      *reinterpret_cast<float4*>(part + ((size_t)(ks * BP + rg * 4 + a)) * N + cg * 4) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_constant__ RhnFwd P) {
+  const int H = P.H, B = P.B, BP = P.BP, T = P.T;
+  const int n0 = blockIdx.x * kNC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long HB = (long long)H * BP;
+  GNAS_DYN_SMEM(float, smem);
+  float* W0s = smem;                          // [2H][8]
+  float* Wss = W0s + (size_t)2 * H * 8;       // [8][H][8]
+  float* abuf = Wss + (size_t)8 * H * 8;      // [2][kKCH][BP]
+  float* part = abuf + 2 * kKCH * BP;         // [KS][BP][N]  (<= BP*64 floats)
+  float* accn = part + BP * 64;               // [8][BP][4]  pending node accumulators
+  float* sloc = accn + 8 * BP * 4;            // [9][BP][4]  own columns of s_0..s_8
+  float* hloc = sloc + 9 * BP * 4;            // [BP][4]     own columns of h_{t-1}
+  float* hml = hloc + BP * 4;                 // [BP][4]     own columns of the hidden mask
+  float* pp = hml + BP * 4;                   // [36][4] probabilities, [36] q
+  float* pq = pp + 36 * 4;
+  float* run = pq + 36;                       // [2][4] running mean | var of own columns
+  __shared__ int s_abort;
+  // ---- one-time setup: weight slices, masks, probability table
+  for (int i = tid; i < 2 * H * 8; i += kThreads) {
+    const int k = i >> 3, c = i & 7;
+    W0s[i] = P.W0[(size_t)k * 2 * H + (c < 4 ? n0 + c : H + n0 + c - 4)];
+  }
+  for (int i = tid; i < 8 * H * 8; i += kThreads) {
+    const int c = i & 7, k = (i >> 3) % H, w = i / (8 * H);
+    Wss[i] = P.Ws[((size_t)w * H + k) * 2 * H + (c < 4 ? n0 + c : H + n0 + c - 4)];
+  }
+  for (int i = tid; i < BP * 4; i += kThreads) {
+    const int m = i >> 2, c = i & 3;
+    hml[i] = P.hmT[(size_t)(n0 + c) * BP + m];
+    hloc[i] = P.h0T[(size_t)(n0 + c) * BP + m];
+  }
+  for (int i = tid; i < 8 * BP * 4; i += kThreads) accn[i] = 0.f;
+  for (int i = tid; i < 9 * BP * 4; i += kThreads) sloc[i] = 0.f;
+  if (tid < 36) {
+    float q = 0.f;
+    for (int k = 0; k < 4; ++k) {
+      const int ix = P.tb.pidx[tid][k];
+      const float v = ix >= 0 ? P.probs[ix] : 0.f;
+      pp[tid * 4 + k] = v; q += v;
+    }
+    pq[tid] = q;
+  }
+  if (tid < 8) run[tid] = P.running ? P.running[(tid >> 2) * H + n0 + (tid & 3)] : (tid < 4 ? 0.f : 1.f);
+  __syncthreads();
+  unsigned bar_target = 0;
+  const float invB = 1.f / (float)B;
+
+  // BatchNorm over the batch for the 4 own columns of `src` ([BP][4]); warp w < 4 handles column w.
+  auto bn_publish = [&](const float* src, int t, int stage) {
+    if (warp < kNC) {
+      const int col = warp;
+      float v0 = lane < B ? src[lane * 4 + col] : 0.f;
+      float v1 = lane + 32 < B ? src[(lane + 32) * 4 + col] : 0.f;
+      float mean, rstd;
+      if (P.training) {
+        mean = warp_sum(v0 + v1) * invB;
+        const float d0 = lane < B ? v0 - mean : 0.f, d1 = lane + 32 < B ? v1 - mean : 0.f;
+        const float var = warp_sum(d0 * d0 + d1 * d1) * invB;
+        rstd = 1.0f / sqrtf(var + kBnEps);
+        if (lane == 0) {
+          run[col] = (1.f - P.momentum) * run[col] + P.momentum * mean;
+          run[4 + col] = (1.f - P.momentum) * run[4 + col] + P.momentum * (B > 1 ? var * (float)B / (float)(B - 1) : var);
+        }
+      } else {
+        mean = run[col];
+        rstd = 1.0f / sqrtf(run[4 + col] + kBnEps);
+      }
+      const int n = n0 + col;
+      if (lane == 0) {
+        float* st = P.stat + ((size_t)t * 9 + stage) * 2 * H;
+        st[n] = mean; st[H + n] = rstd;
+      }
+      float* STr = P.ST + ((size_t)t * 9 + stage) * HB + (size_t)n * BP;
+      float* rgr = P.ring + (size_t)stage * HB + (size_t)n * BP;
+      for (int m = lane; m < BP; m += 32) {
+        const float v = m < B ? ((m < 32 ? v0 : v1) - mean) * rstd : 0.f;
+        sloc[(stage * BP + m) * 4 + col] = v;
+        STr[m] = v;
+        rgr[m] = v * hml[m * 4 + col];
+      }
+    }
+  };
+
+  for (int t = 0; t < T; ++t) {
+    // ---------------- stage 0: [c0|h0] = [x_t*xm | h*hm] W0 ; s_0 = BN(h + sig(c0)(tanh(h0) - h))
+    rhn_gemm(P.xmT + (size_t)t * HB, P.ring + 9 * HB, H, 2 * H, BP, 8, W0s, 0, H, true, abuf, part);
+    {
+      const int KS = rhn_ks(BP, 8);
+      float* tmp = accn;   // borrow node-0..: use part tail instead? accn[0] is empty at this point of the step
+      for (int i = tid; i < B * 4; i += kThreads) {
+        const int col = i / B, m = i - col * B;
+        float c = 0.f, h = 0.f;
+        for (int s = 0; s < KS; ++s) { c += part[(size_t)(s * BP + m) * 8 + col]; h += part[(size_t)(s * BP + m) * 8 + 4 + col]; }
+        P.C0T[((size_t)t * 2 + 0) * HB + (size_t)(n0 + col) * BP + m] = c;
+        P.C0T[((size_t)t * 2 + 1) * HB + (size_t)(n0 + col) * BP + m] = h;
+        const float hp = hloc[m * 4 + col];
+        tmp[(7 * BP + m) * 4 + col] = hp + sigmoidf_(c) * (tanhf(h) - hp);   // node-7 slot is untouched until stage 0 GEMM of s_0 is consumed
+      }
+      __syncthreads();
+      bn_publish(accn + 7 * BP * 4, t, 0);
+      __syncthreads();
+      for (int i = tid; i < BP * 4; i += kThreads) accn[7 * BP * 4 + i] = 0.f;
+    }
+    bar_target += gridDim.x;
+    if (grid_barrier(P.bar, P.abort_flag, bar_target, &s_abort)) return;
+    // ---------------- stages j = 0..7: multiply s_j with the slices of Ws[j..7], finish node j -> s_{j+1}
+    for (int j = 0; j < 8; ++j) {
+      const int N = 8 * (8 - j);
+      rhn_gemm(P.ring + (size_t)j * HB, nullptr, H, H, BP, N, Wss + (size_t)j * H * 8, H * 8, H, false, abuf, part);
+      const int KS = rhn_ks(BP, N);
+      const int items = (8 - j) * 4 * B;
+      for (int it = tid; it < items; it += kThreads) {
+        const int m = it % B;
+        const int col = (it / B) & 3;
+        const int irel = it / (4 * B);
+        const int i = j + irel;
+        const int p = i * (i + 1) / 2 + j;
+        float c = 0.f, h = 0.f;
+        for (int s = 0; s < KS; ++s) {
+          c += part[(size_t)(s * BP + m) * N + irel * 8 + col];
+          h += part[(size_t)(s * BP + m) * N + irel * 8 + 4 + col];
+        }
+        float* chp = P.CHT + (((size_t)t * 36 + p) * 2) * HB + (size_t)(n0 + col) * BP + m;
+        chp[0] = c; chp[HB] = h;
+        const float q = pq[p];
+        if (q != 0.f || pp[p * 4] != 0.f || pp[p * 4 + 1] != 0.f || pp[p * 4 + 2] != 0.f || pp[p * 4 + 3] != 0.f) {
+          const float sj = sloc[(j * BP + m) * 4 + col];
+          const float g = sigmoidf_(c);
+          float F = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { const float pk = pp[p * 4 + k]; if (pk != 0.f) F = fmaf(pk, act_f(k, h), F); }
+          accn[(i * BP + m) * 4 + col] += q * sj + g * (F - q * sj);
+        }
+      }
+      __syncthreads();
+      bn_publish(accn + j * BP * 4, t, j + 1);
+      __syncthreads();
+      for (int i = tid; i < BP * 4; i += kThreads) accn[j * BP * 4 + i] = 0.f;
+      if (j == 7) {
+        // h_t = mean(s_1..s_8)  (model_search.py:96)
+        for (int i = tid; i < BP * 4; i += kThreads) {
+          const int m = i >> 2, col = i & 3;
+          float a = 0.f;
+#pragma unroll
+          for (int s = 1; s <= 8; ++s) a += sloc[(s * BP + m) * 4 + col];
+          a *= 0.125f;
+          if (m >= B) a = 0.f;
+          hloc[i] = a;
+          P.HT[(size_t)t * HB + (size_t)(n0 + col) * BP + m] = a;
+          P.ring[9 * HB + (size_t)(n0 + col) * BP + m] = a * hml[i];
+        }
+        __syncthreads();
+        for (int m = tid; m < B; m += kThreads)
+          *reinterpret_cast<float4*>(P.out + ((size_t)t * B + m) * H + n0) =
+              make_float4(hloc[m * 4], hloc[m * 4 + 1], hloc[m * 4 + 2], hloc[m * 4 + 3]);
+      }
+      bar_target += gridDim.x;
+      if (j < 7 || t + 1 < T) { if (grid_barrier(P.bar, P.abort_flag, bar_target, &s_abort)) return; }
+    }
+  }
+  if (P.training && P.running && tid < 8) P.running[(tid >> 2) * H + n0 + (tid & 3)] = run[tid];
+}
+
+// ------------------------------------------------------------------ backward: per-step kernels
+struct RhnBwd {
+  int T, B, BP, H, t, node;           // node i+1 in 1..8 (elem) ; t current time step
+  const float* ST; float* CHT; float* C0T; const float* HT; const float* h0T; const float* stat;
+  const float* probs; const float* dout;
+  float* dsT; float* dh_cur; float* dh_next;
+  double* dpacc;
+  RhnTable tb;
+};
+
+// dh[n][m] = dout[t][m][n]
+static __global__ void __launch_bounds__(256) k_rhn_dout_T(const float* dout, float* dh, int B, int BP, int H, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < H * BP) { const int n = i / BP, m = i - n * BP; dh[i] = m < B ? dout[((size_t)t * B + m) * H + n] : 0.f; }
+}
+
+// ds_k = dh/8 for k = 1..8, ds_0 = 0
+static __global__ void __launch_bounds__(256) k_rhn_bwd_tinit(float* dsT, const float* dh, long long HB) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 9 * HB; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i / HB);
+    dsT[i] = k == 0 ? 0.f : 0.125f * dh[i - (long long)k * HB];
+  }
+}
+
+// node = i+1: dr = BN_bwd(ds_{i+1}); per edge (i,j): dc, dh (in place over c, h), direct ds_j term, dprobs
+static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem(const __grid_constant__ RhnBwd P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 8 + warp;
+  const int i = P.node - 1;
+  const int B = P.B, BP = P.BP, H = P.H;
+  const long long HB = (long long)H * BP;
+  __shared__ float red[8][8][4];
+  for (int q = threadIdx.x; q < 8 * 8 * 4; q += kThreads) (&red[0][0][0])[q] = 0.f;
+  __syncthreads();
+  if (n < H) {
+    const size_t row = (size_t)n * BP;
+    const float* dsr = P.dsT + (size_t)P.node * HB + row;
+    const float* shr = P.ST + ((size_t)P.t * 9 + P.node) * HB + row;
+    const float rstd = P.stat[((size_t)P.t * 9 + P.node) * 2 * H + H + n];
+    const bool r0 = lane < B, r1 = lane + 32 < B;
+    const float d0 = r0 ? dsr[lane] : 0.f, d1 = r1 ? dsr[lane + 32] : 0.f;
+    const float h0 = r0 ? shr[lane] : 0.f, h1 = r1 ? shr[lane + 32] : 0.f;
+    const float S1 = warp_sum(d0 + d1) / (float)B;
+    const float S2 = warp_sum(d0 * h0 + d1 * h1) / (float)B;
+    const float dr0 = rstd * (d0 - S1 - h0 * S2), dr1 = rstd * (d1 - S1 - h1 * S2);
+    for (int j = 0; j <= i; ++j) {
+      const int p = i * (i + 1) / 2 + j;
+      float pk[4], dpl[4] = {0.f, 0.f, 0.f, 0.f}, q = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int ix = P.tb.pidx[p][k]; pk[k] = ix >= 0 ? P.probs[ix] : 0.f; q += pk[k]; }
+      float* cp = P.CHT + (((size_t)P.t * 36 + p) * 2) * HB + row;
+      float* hp = cp + HB;
+      const float* sjr = P.ST + ((size_t)P.t * 9 + j) * HB + row;
+      float* dsj = P.dsT + (size_t)j * HB + row;
+      for (int half = 0; half < 2; ++half) {
+        const int m = lane + 32 * half;
+        if (m >= BP) continue;
+        float dc = 0.f, dh = 0.f;
+        if (m < B) {
+          const float dr = half ? dr1 : dr0;
+          const float c = cp[m], h = hp[m], sj = sjr[m];
+          const float g = sigmoidf_(c);
+          float F = 0.f, Fp = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (P.tb.pidx[p][k] >= 0) {
+              const float f = act_f(k, h);
+              F = fmaf(pk[k], f, F); Fp = fmaf(pk[k], act_df(k, h), Fp);
+              dpl[k] = fmaf(dr, sj + g * (f - sj), dpl[k]);
+            }
+          }
+          dc = dr * g * (1.f - g) * (F - q * sj);
+          dh = dr * g * Fp;
+          dsj[m] += dr * q * (1.f - g);
+        }
+        cp[m] = dc; hp[m] = dh;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float v = warp_sum(dpl[k]); if (lane == 0) red[warp][j][k] = v; }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int j = threadIdx.x >> 2, k = threadIdx.x & 3;
+    if (j <= i) {
+      float v = 0.f;
+      for (int w = 0; w < 8; ++w) v += red[w][j][k];
+      const int p = i * (i + 1) / 2 + j;
+      if (P.tb.pidx[p][k] >= 0) atomicAdd(&P.dpacc[p * 4 + k], (double)v);
+    }
+  }
+}
+
+// stage 0: dr0 = BN_bwd(ds_0); dh_prev direct term (+ dout[t-1]); dc0, dh0 in place over C0T
+static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem0(const __grid_constant__ RhnBwd P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 8 + warp;
+  const int B = P.B, BP = P.BP, H = P.H;
+  const long long HB = (long long)H * BP;
+  if (n >= H) return;
+  const size_t row = (size_t)n * BP;
+  const float* dsr = P.dsT + row;
+  const float* shr = P.ST + ((size_t)P.t * 9) * HB + row;
+  const float rstd = P.stat[((size_t)P.t * 9) * 2 * H + H + n];
+  const bool r0 = lane < B, r1 = lane + 32 < B;
+  const float d0 = r0 ? dsr[lane] : 0.f, d1 = r1 ? dsr[lane + 32] : 0.f;
+  const float s0 = r0 ? shr[lane] : 0.f, s1 = r1 ? shr[lane + 32] : 0.f;
+  const float S1 = warp_sum(d0 + d1) / (float)B;
+  const float S2 = warp_sum(d0 * s0 + d1 * s1) / (float)B;
+  float* cp = P.C0T + ((size_t)P.t * 2) * HB + row;
+  float* hp = cp + HB;
+  const float* hprev = (P.t > 0 ? P.HT + (size_t)(P.t - 1) * HB : P.h0T) + row;
+  for (int half = 0; half < 2; ++half) {
+    const int m = lane + 32 * half;
+    if (m >= BP) continue;
+    float dc = 0.f, dh = 0.f, dhp = 0.f;
+    if (m < B) {
+      const float dr = rstd * ((half ? d1 : d0) - S1 - (half ? s1 : s0) * S2);
+      const float c = cp[m], h = hp[m], hv = hprev[m];
+      const float g = sigmoidf_(c), v = tanhf(h);
+      dhp = dr * (1.f - g);
+      dc = dr * g * (1.f - g) * (v - hv);
+      dh = dr * g * (1.f - v * v);
+      if (P.t > 0) dhp += P.dout[((size_t)(P.t - 1) * B + m) * H + n];
+    }
+    cp[m] = dc; hp[m] = dh;
+    P.dh_next[row + m] = dhp;
+  }
+}
+
+// out_z[n][m] += mask[n][m] * sum_k W[n][k] * D_z[k][m]   (split-K, atomics)
+struct RhnGemm {
+  int Nrows, K, BP, nz, ksplit, Hsplit;   // rows >= Hsplit go to out2/mask2 (stage 0: dx rows | dh rows)
+  const float* W; int ldw;
+  const float* D[8]; float* out[8];
+  const float* mask; float* out2; const float* mask2;
+};
+static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_gemm(const __grid_constant__ RhnGemm P) {
+  const int z = blockIdx.z;
+  const int n0 = blockIdx.x * 32;
+  const int kper = P.K / P.ksplit;
+  const int kbeg = blockIdx.y * kper;
+  const int BP = P.BP;
+  const int tid = threadIdx.x;
+  const int ncg = BP / 4;
+  const int rp = tid / ncg, cg = tid - rp * ncg;
+  const bool active = rp < 16;
+  __shared__ float Wt[32][34];
+  GNAS_DYN_SMEM(float, Ds);    // [32][BP]
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const float* Dz = P.D[z];
+  for (int k0 = kbeg; k0 < kbeg + kper; k0 += 32) {
+    for (int i = tid; i < 32 * 32; i += kThreads) {
+      const int r = i >> 5, k = i & 31;
+      Wt[k][r] = (n0 + r < P.Nrows) ? P.W[(size_t)(n0 + r) * P.ldw + k0 + k] : 0.f;
+    }
+    for (int i = tid; i < 32 * BP / 4; i += kThreads)
+      reinterpret_cast<float4*>(Ds)[i] = reinterpret_cast<const float4*>(Dz + (size_t)k0 * BP)[i];
+    __syncthreads();
+    if (active) {
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        const float w0 = Wt[k][2 * rp], w1 = Wt[k][2 * rp + 1];
+        const float4 d = *reinterpret_cast<const float4*>(Ds + k * BP + 4 * cg);
+        acc[0][0] = fmaf(w0, d.x, acc[0][0]); acc[0][1] = fmaf(w0, d.y, acc[0][1]); acc[0][2] = fmaf(w0, d.z, acc[0][2]); acc[0][3] = fmaf(w0, d.w, acc[0][3]);
+        acc[1][0] = fmaf(w1, d.x, acc[1][0]); acc[1][1] = fmaf(w1, d.y, acc[1][1]); acc[1][2] = fmaf(w1, d.z, acc[1][2]); acc[1][3] = fmaf(w1, d.w, acc[1][3]);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int n = n0 + 2 * rp + a;
+      if (n >= P.Nrows) continue;
+      float* o; const float* mk;
+      if (n < P.Hsplit) { o = P.out[z] + (size_t)n * BP; mk = P.mask + (size_t)n * BP; }
+      else { o = P.out2 + (size_t)(n - P.Hsplit) * BP; mk = P.mask2 + (size_t)(n - P.Hsplit) * BP; }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) atomicAdd(&o[4 * cg + b], mk[4 * cg + b] * acc[a][b]);
+    }
+  }
+}
+
+// dW[n][k'] += sum over blocks, sum_m A[n][m] * D[k'][m];  A = mask .* S (or the stage-0 input rows)
+struct RhnWg {
+  int T, B, BP, H, tsplit, is_w0;
+  const float* ST; const float* CHT; const float* C0T; const float* HT; const float* h0T;
+  const float* xmT; const float* hmT;
+  float* dW0; float* dWs;
+};
+static __global__ void __launch_bounds__(kThreads) k_rhn_wgrad(const __grid_constant__ RhnWg P) {
+  const int H = P.H, BP = P.BP, B = P.B;
+  const long long HB = (long long)H * BP;
+  const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const int iw = P.is_w0 ? 0 : (int)(blockIdx.z % 8);
+  const int ts = P.is_w0 ? blockIdx.z : blockIdx.z / 8;
+  const int tper = (P.T + P.tsplit - 1) / P.tsplit;
+  const int tb = ts * tper, te = min(P.T, tb + tper);
+  const int Nrows = P.is_w0 ? 2 * H : H;
+  const int tid = threadIdx.x, tr = tid >> 4, tc = tid & 15;
+  __shared__ float As[64][68];   // [m][n]
+  __shared__ float Ds[64][68];   // [m][k']
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const int nblk = P.is_w0 ? 1 : iw + 1;
+  for (int t = tb; t < te; ++t) {
+    for (int j = 0; j < nblk; ++j) {
+      const float* Dsrc = P.is_w0 ? P.C0T + ((size_t)t * 2) * HB : P.CHT + (((size_t)t * 36 + iw * (iw + 1) / 2 + j) * 2) * HB;
+      for (int i = tid; i < 64 * BP; i += kThreads) {
+        const int r = i / BP, m = i - r * BP;
+        const int n = n0 + r;
+        float a = 0.f;
+        if (n < Nrows && m < B) {
+          if (P.is_w0) {
+            if (n < H) a = P.xmT[(size_t)t * HB + (size_t)n * BP + m];
+            else {
+              const size_t o = (size_t)(n - H) * BP + m;
+              a = (t > 0 ? P.HT[(size_t)(t - 1) * HB + o] : P.h0T[o]) * P.hmT[o];
+            }
+          } else {
+            const size_t o = (size_t)n * BP + m;
+            a = P.ST[((size_t)t * 9 + j) * HB + o] * P.hmT[o];
+          }
+        }
+        As[m][r] = a;
+        Ds[m][r] = (m < B) ? Dsrc[(size_t)(k0 + r) * BP + m] : 0.f;
+      }
+      __syncthreads();
+      for (int m = 0; m < BP; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[m][4 * tr]);
+        const float4 d = *reinterpret_cast<const float4*>(&Ds[m][4 * tc]);
+        acc[0][0] = fmaf(a.x, d.x, acc[0][0]); acc[0][1] = fmaf(a.x, d.y, acc[0][1]); acc[0][2] = fmaf(a.x, d.z, acc[0][2]); acc[0][3] = fmaf(a.x, d.w, acc[0][3]);
+        acc[1][0] = fmaf(a.y, d.x, acc[1][0]); acc[1][1] = fmaf(a.y, d.y, acc[1][1]); acc[1][2] = fmaf(a.y, d.z, acc[1][2]); acc[1][3] = fmaf(a.y, d.w, acc[1][3]);
+        acc[2][0] = fmaf(a.z, d.x, acc[2][0]); acc[2][1] = fmaf(a.z, d.y, acc[2][1]); acc[2][2] = fmaf(a.z, d.z, acc[2][2]); acc[2][3] = fmaf(a.z, d.w, acc[2][3]);
+        acc[3][0] = fmaf(a.w, d.x, acc[3][0]); acc[3][1] = fmaf(a.w, d.y, acc[3][1]); acc[3][2] = fmaf(a.w, d.z, acc[3][2]); acc[3][3] = fmaf(a.w, d.w, acc[3][3]);
+      }
+      __syncthreads();
+    }
+  }
+  float* dW = P.is_w0 ? P.dW0 : P.dWs + (size_t)iw * H * 2 * H;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int n = n0 + 4 * tr + a;
+    if (n >= Nrows) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int k = k0 + 4 * tc + b;
+      if (k < 2 * H) atomicAdd(&dW[(size_t)n * 2 * H + k], acc[a][b]);
+    }
+  }
+}
+
+static __global__ void k_rhn_dprobs(const double* dpacc, float* dprobs, int nprobs, RhnTable tb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nprobs) dprobs[i] = 0.f;
+  __syncthreads();
+  if (i < 36 * 4) {
+    const int ix = tb.pidx[i >> 2][i & 3];
+    if (ix >= 0) dprobs[ix] = (float)dpacc[i];
+  }
+}
+
+static int rhn_validate(const GnasRhnDesc* d) {
+  if (!d) { set_error("null descriptor"); return GNAS_ERR_ARG; }
+  if (d->T <= 0 || d->B <= 0 || d->H <= 0) { set_error("rhn: bad shape"); return GNAS_ERR_SHAPE; }
+  if (d->H % kKCH != 0) { set_error("rhn: hidden size must be a multiple of 32"); return GNAS_ERR_SHAPE; }
+  if ((d->B + 3) / 4 * 4 > kMaxBP) { set_error("rhn: at most 64 batch rows per GPU"); return GNAS_ERR_SHAPE; }
+  return 0;
+}
+
+static inline int ewb(long long total) {
+  long long nb = (total + 255) / 256;
+  return (int)(nb < 1 ? 1 : (nb > 148 * 8 ? 148 * 8 : nb));
+}
+
+}  // namespace gnas
+
 using namespace gnas;
-extern "C" int gnas_rhn_workspace(const GnasRhnDesc*, int64_t*, int64_t*) { set_error("rhn: not built"); return GNAS_ERR_UNSUPPORTED; }
-extern "C" int gnas_rhn_forward(const GnasRhnDesc*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, void*) { set_error("rhn: not built"); return GNAS_ERR_UNSUPPORTED; }
-extern "C" int gnas_rhn_backward(const GnasRhnDesc*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*, float*, float*, int, void*) { set_error("rhn: not built"); return GNAS_ERR_UNSUPPORTED; }
+
+extern "C" int gnas_rhn_workspace(const GnasRhnDesc* d, int64_t* fwd_floats, int64_t* bwd_floats) {
+  int rc = rhn_validate(d);
+  if (rc) return rc;
+  RhnPlan p = rhn_plan(d);
+  if (fwd_floats) *fwd_floats = p.fwd_total;
+  if (bwd_floats) *bwd_floats = p.bwd_total;
+  return 0;
+}
+
+extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const float* h0, const float* W0,
+                                const float* Ws, const float* probs, const float* x_mask, const float* h_mask,
+                                float* bn_running, float* out, float* ws, void* stream) {
+  int rc = rhn_validate(d);
+  if (rc) return rc;
+  if (!x || !h0 || !W0 || !Ws || !probs || !out || !ws) { set_error("rhn_forward: null pointer"); return GNAS_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  RhnPlan p = rhn_plan(d);
+  const int H = d->H, BP = p.BP;
+  const long long HB = (long long)H * BP;
+  RhnPro pro;
+  pro.T = d->T; pro.B = d->B; pro.BP = BP; pro.H = H;
+  pro.x = x; pro.h0 = h0; pro.xm = d->training ? x_mask : nullptr; pro.hm = d->training ? h_mask : nullptr;
+  pro.xmT = ws + p.xmT; pro.xkT = ws + p.xkT; pro.hmT = ws + p.hmT; pro.h0T = ws + p.h0T; pro.ring9 = ws + p.ring + 9 * HB;
+  GNAS_LAUNCH(k_rhn_prologue, dim3(ewb((long long)(d->T + 3) * HB)), dim3(256), 0, st, pro);
+  cudaMemsetAsync(ws + p.bar, 0, 64 * sizeof(float), st);
+  RhnFwd f;
+  f.T = d->T; f.B = d->B; f.BP = BP; f.H = H; f.training = d->training; f.momentum = d->bn_momentum;
+  f.xmT = ws + p.xmT; f.hmT = ws + p.hmT; f.h0T = ws + p.h0T; f.W0 = W0; f.Ws = Ws; f.probs = probs;
+  f.ring = ws + p.ring; f.ST = ws + p.ST; f.CHT = ws + p.CHT; f.C0T = ws + p.C0T; f.HT = ws + p.HT; f.stat = ws + p.stat;
+  f.out = out; f.running = bn_running;
+  f.bar = reinterpret_cast<unsigned*>(ws + p.bar); f.abort_flag = reinterpret_cast<int*>(ws + p.bar) + 8;
+  rhn_table(d, f.tb);
+  const size_t smem = sizeof(float) * ((size_t)2 * H * 8 + (size_t)8 * H * 8 + 2 * kKCH * BP + (size_t)BP * 64 +
+                                       8 * BP * 4 + 9 * BP * 4 + 2 * BP * 4 + 36 * 5 + 8 + 8);
+  const int grid = H / kNC;
+#ifdef GNAS_EMUL
+  GNAS_LAUNCH_COOP(k_rhn_forward, dim3(grid), dim3(kThreads), smem, st, f);
+#else
+  {
+    static size_t prepared = 0;
+    if (smem > prepared) {
+      cudaError_t e = cudaFuncSetAttribute(k_rhn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("rhn_forward: shared memory request rejected"); return (int)e; }
+      prepared = smem;
+    }
+    int dev = 0, nsm = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rhn_forward, kThreads, smem);
+    if (per_sm * nsm < grid) { set_error("rhn_forward: grid does not fit co-resident (hidden size too large)"); return GNAS_ERR_UNSUPPORTED; }
+    void* args[] = {(void*)&f};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_rhn_forward, dim3(grid), dim3(kThreads), args, smem, st);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
+  }
+#endif
+  return check_launch("gnas_rhn_forward");
+}
+
+extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const float* h0, const float* W0,
+                                 const float* Ws, const float* probs, const float* x_mask, const float* h_mask,
+                                 const float* dout, float* ws, float* scratch, float* dx, float* dh0,
+                                 float* dW0, float* dWs, float* dprobs, int need_wgrad, void* stream) {
+  int rc = rhn_validate(d);
+  if (rc) return rc;
+  (void)x; (void)h0; (void)x_mask; (void)h_mask;
+  if (!W0 || !Ws || !probs || !dout || !ws || !scratch || !dx || !dh0 || !dprobs || (need_wgrad && (!dW0 || !dWs))) {
+    set_error("rhn_backward: null pointer"); return GNAS_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  RhnPlan p = rhn_plan(d);
+  const int H = d->H, BP = p.BP, B = d->B, T = d->T;
+  const long long HB = (long long)H * BP;
+  RhnTable tb;
+  rhn_table(d, tb);
+  cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)p.bwd_total, st);
+  float* dhbuf[2] = {scratch + p.dhT, scratch + p.dhT + HB};
+  // dh for the last step = dout[T-1]^T
+  GNAS_LAUNCH(k_rhn_dout_T, dim3((H * BP + 255) / 256), dim3(256), 0, st, dout, dhbuf[0], B, BP, H, T - 1);
+  RhnBwd bp;
+  bp.T = T; bp.B = B; bp.BP = BP; bp.H = H;
+  bp.ST = ws + p.ST; bp.CHT = ws + p.CHT; bp.C0T = ws + p.C0T; bp.HT = ws + p.HT; bp.h0T = ws + p.h0T; bp.stat = ws + p.stat;
+  bp.probs = probs; bp.dout = dout; bp.dsT = scratch + p.dsT; bp.dpacc = reinterpret_cast<double*>(scratch + p.dpacc);
+  bp.tb = tb;
+  const int eb = (H + 7) / 8;
+  const size_t gsm = sizeof(float) * 32 * BP;
+  for (int t = T - 1; t >= 0; --t) {
+    float* dh_cur = dhbuf[(T - 1 - t) & 1];
+    float* dh_next = dhbuf[(T - t) & 1];
+    bp.t = t; bp.dh_cur = dh_cur; bp.dh_next = dh_next;
+    GNAS_LAUNCH(k_rhn_bwd_tinit, dim3(ewb(9 * HB)), dim3(256), 0, st, scratch + p.dsT, (const float*)dh_cur, HB);
+    for (int i = 7; i >= 0; --i) {
+      bp.node = i + 1;
+      GNAS_LAUNCH(k_rhn_bwd_elem, dim3(eb), dim3(kThreads), 0, st, bp);
+      RhnGemm g;
+      g.Nrows = H; g.K = 2 * H; g.BP = BP; g.nz = i + 1; g.ksplit = (2 * H) / 32 >= 8 ? 8 : 1; g.Hsplit = H;
+      g.W = Ws + (size_t)i * H * 2 * H; g.ldw = 2 * H;
+      for (int j = 0; j <= i; ++j) {
+        g.D[j] = ws + p.CHT + (((size_t)t * 36 + i * (i + 1) / 2 + j) * 2) * HB;
+        g.out[j] = scratch + p.dsT + (size_t)j * HB;
+      }
+      g.mask = ws + p.hmT; g.out2 = nullptr; g.mask2 = nullptr;
+      GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((H + 31) / 32, g.ksplit, i + 1), dim3(kThreads), gsm, st, g);
+    }
+    GNAS_LAUNCH(k_rhn_bwd_elem0, dim3(eb), dim3(kThreads), 0, st, bp);
+    RhnGemm g;
+    g.Nrows = 2 * H; g.K = 2 * H; g.BP = BP; g.nz = 1; g.ksplit = (2 * H) / 32 >= 8 ? 8 : 1; g.Hsplit = H;
+    g.W = W0; g.ldw = 2 * H;
+    g.D[0] = ws + p.C0T + ((size_t)t * 2) * HB;
+    g.out[0] = scratch + p.dxT + (size_t)t * HB; g.mask = ws + p.xkT;
+    g.out2 = dh_next; g.mask2 = ws + p.hmT;
+    GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((2 * H + 31) / 32, g.ksplit, 1), dim3(kThreads), gsm, st, g);
+  }
+  // outputs: dx [T][B][H], dh0 [B][H], dprobs
+  GNAS_LAUNCH(k_rhn_untranspose, dim3(ewb((long long)T * B * H)), dim3(256), 0, st, (const float*)(scratch + p.dxT), dx, T, B, BP, H);
+  GNAS_LAUNCH(k_rhn_untranspose, dim3(ewb((long long)B * H)), dim3(256), 0, st, (const float*)dhbuf[T & 1], dh0, 1, B, BP, H);
+  GNAS_LAUNCH(k_rhn_dprobs, dim3(1), dim3(256), 0, st, (const double*)(scratch + p.dpacc), dprobs, 36 * d->n_prims, tb);
+  if (need_wgrad) {
+    RhnWg w;
+    w.T = T; w.B = B; w.BP = BP; w.H = H;
+    w.ST = ws + p.ST; w.CHT = ws + p.CHT; w.C0T = ws + p.C0T; w.HT = ws + p.HT; w.h0T = ws + p.h0T;
+    w.xmT = ws + p.xmT; w.hmT = ws + p.hmT; w.dW0 = dW0; w.dWs = dWs;
+    w.tsplit = T >= 6 ? 6 : 1;
+    w.is_w0 = 0;
+    GNAS_LAUNCH(k_rhn_wgrad, dim3((H + 63) / 64, (2 * H + 63) / 64, 8 * w.tsplit), dim3(kThreads), 0, st, w);
+    w.is_w0 = 1;
+    GNAS_LAUNCH(k_rhn_wgrad, dim3((2 * H + 63) / 64, (2 * H + 63) / 64, w.tsplit), dim3(kThreads), 0, st, w);
+  }
+  return check_launch("gnas_rhn_backward");
+}
