@@ -7,5 +7,9 @@ DARTSCellSearch, RNNModelSearch (model_search.py), Architect (darts_tools/archit
 from . import _lib  # noqa: F401
 from .cnn import CNN_Cell_search, MixedOp  # noqa: F401
 from .operations import OPS, PRIMITIVES_cnn, PRIMITIVES_rnn  # noqa: F401
+from .rnn import DARTSCellSearch  # noqa: F401
+from .model import Genotype, RNNModel, RNNModelSearch  # noqa: F401
+from .architect import Architect  # noqa: F401
+from .train import Hyper, SearchStep, train  # noqa: F401
 
 __version__ = "0.1.0"

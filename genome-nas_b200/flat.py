@@ -48,8 +48,9 @@ def _alias(t, total):
 class FlatRegion:
     """Contiguous storage for one module tree (a MixedOp, a cell, an RHN layer or the whole supernet)."""
 
-    def __init__(self, module):
+    def __init__(self, module, exclude=()):
         self.module = module
+        self.exclude = tuple(exclude)   # parameter names owned by an enclosing module (e.g. the shared RNN alphas)
         self.flat = None      # parameters
         self.gflat = None     # gradients
         self.bn = None        # running_mean | running_var of every BatchNorm, in registration order
@@ -67,13 +68,13 @@ class FlatRegion:
 
     def _make_probe(self, bufs):
         p = self._params
-        probe = (p[0].data_ptr(), p[-1].data_ptr(), p[0].device, len(p)) if p else ()
+        probe = (p[0].device, len(p)) + tuple(q.data_ptr() for q in p[::61]) + (p[-1].data_ptr(),) if p else ()
         if bufs:
             probe += (bufs[0][1].data_ptr(), bufs[-1][1].data_ptr(), bufs[0][1].device)
         return probe
 
     def ensure(self):
-        named = list(self.module.named_parameters())
+        named = [(n, p) for n, p in self.module.named_parameters() if n not in self.exclude]
         self._names = [n for n, _ in named]
         self._params = [p for _, p in named]
         bufs = self._bufs()
@@ -159,9 +160,9 @@ class FlatRegion:
         self.gflat.zero_()
 
 
-def region_of(module) -> FlatRegion:
+def region_of(module, exclude=()) -> FlatRegion:
     r = module.__dict__.get("_gnas_region")
     if r is None:
-        r = FlatRegion(module)
+        r = FlatRegion(module, exclude)
         module.__dict__["_gnas_region"] = r
     return r.ensure()

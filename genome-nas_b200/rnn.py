@@ -30,7 +30,7 @@ class _RhnFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, x, h0, probs, x_mask, h_mask, _anchor):
         lib = _lib.lib()
-        region = region_of(mod)
+        region = region_of(mod, exclude=('weights',))
         x = _lib.require(x.contiguous(), "inputs")
         h0 = _lib.require(h0.contiguous(), "hidden")
         probs = _lib.require(probs.detach().contiguous(), "probs")
@@ -68,7 +68,7 @@ class _RhnFunction(torch.autograd.Function):
         x, h0, probs, ws = ctx.saved_tensors
         x_mask, h_mask = ctx.masks
         dout = _lib.require(dout.contiguous(), "grad_output")
-        region = region_of(mod)
+        region = region_of(mod, exclude=('weights',))
         flat, off = region.flat, region.offsets
         dw0 = dws = None
         if ctx.need_wgrad:

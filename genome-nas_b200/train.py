@@ -1,0 +1,166 @@
+"""The supernet search step: alpha step + weight step.
+
+`train()` keeps the reference's entry point (generalNAS_tools/train_and_validate.py:38-179) for the
+genomeDARTS configuration (train_arch, first-order Architect or the P-DARTS inline alpha step).
+`SearchStep` is the same arithmetic with the optimiser work done by the flat-buffer kernels
+(gnas_grad_sumsq / gnas_sgd_step / gnas_adam_step) and an optional NCCL allreduce of the flat
+gradient buffer for batch-sharded data parallelism; it is what bench.py times.
+"""
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+class Hyper:
+    """README.md:72 / train_genomicDARTS.py:53-140."""
+    cnn_lr = 0.025
+    cnn_wd = 3e-4
+    momentum = 0.9
+    rhn_lr = 8.0
+    rhn_wd = 5e-7
+    clip = 0.25
+    beta = 1e-3
+    arch_lr = 3e-3
+    arch_wd = 1e-3
+    adam_betas = (0.9, 0.999)
+    adam_eps = 1e-8
+
+
+def tar_loss(rnn_h, beta):
+    """Temporal activation regularisation, train_and_validate.py:140."""
+    return beta * (rnn_h[1:] - rnn_h[:-1]).pow(2).mean()
+
+
+class SearchStep:
+    """One genomeDARTS search iteration on the flat buffers of an RNNModelSearch."""
+
+    def __init__(self, model, hyper=None, process_group=None, world_size=1):
+        self.model, self.h = model, hyper or Hyper()
+        self.pg, self.world = process_group, world_size
+        self.region = model.flat_region()
+        self.region.ensure_grads()
+        off = self.region.offsets
+        self.n_alpha = off["stem.0.weight"]                      # alphas_normal | alphas_reduce | weights (padded)
+        self.rhn_lo, self.rhn_hi = off["rnns.0._W0"], off["decoder.weight"]
+        self.total = self.region.total
+        dev = self.region.flat.device
+        self.mom = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(self.n_alpha, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(self.n_alpha, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.t_adam = 0
+        self.first_sgd = True
+
+    def _refresh(self):
+        r = self.model.flat_region()
+        if r.flat.data_ptr() != self.region.flat.data_ptr():
+            raise RuntimeError("model parameters were re-allocated: build a new SearchStep")
+        return r.flat, r.ensure_grads()
+
+    def alpha_step(self, x_valid, y_valid):
+        lib, h = _lib.lib(), self.h
+        flat, g = self._refresh()
+        model = self.model
+        g[:self.n_alpha].zero_()
+        model.set_weight_grads(False)
+        try:
+            logits, _ = model(x_valid, model.init_hidden(x_valid.size(0)))
+            loss = F.binary_cross_entropy(logits, y_valid)
+            loss.backward()
+        finally:
+            model.set_weight_grads(True)
+        ga = g[:self.n_alpha]
+        if self.world > 1:
+            torch.distributed.all_reduce(ga, group=self.pg)
+            ga.div_(self.world)
+        self.t_adam += 1
+        _lib.check(lib.gnas_adam_step(_lib.ptr(flat), _lib.ptr(ga), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v),
+                                      self.n_alpha, h.arch_lr, h.arch_wd, h.adam_betas[0], h.adam_betas[1], h.adam_eps,
+                                      self.t_adam, _lib.stream_ptr(flat)), "adam_step")
+        _lib.LAUNCHES += 1
+        return loss.detach()
+
+    def weight_step(self, x_train, y_train):
+        lib, h = _lib.lib(), self.h
+        flat, g = self._refresh()
+        model = self.model
+        g.zero_()
+        logits, hidden, rnn_hs, _ = model(x_train, model.init_hidden(x_train.size(0)), return_h=True)
+        raw = F.binary_cross_entropy(logits, y_train)
+        loss = raw + tar_loss(rnn_hs[-1], h.beta)
+        loss.backward()
+        if self.world > 1:
+            torch.distributed.all_reduce(g, group=self.pg)
+            g.div_(self.world)
+        st = _lib.stream_ptr(flat)
+        self.sumsq.zero_()
+        _lib.check(lib.gnas_grad_sumsq(_lib.ptr(g), self.total, _lib.ptr(self.sumsq), st), "grad_sumsq")
+        first = 1 if self.first_sgd else 0
+        for lo, hi in ((0, self.rhn_lo), (self.rhn_hi, self.total)):      # "conv" group: everything but rnns.*
+            _lib.check(lib.gnas_sgd_step(_lib.ptr(flat[lo:]), _lib.ptr(g[lo:]), _lib.ptr(self.mom[lo:]), hi - lo,
+                                         h.cnn_lr, h.cnn_wd, h.momentum, first, _lib.ptr(self.sumsq), h.clip, st),
+                       "sgd_step")
+        _lib.check(lib.gnas_sgd_step(_lib.ptr(flat[self.rhn_lo:]), _lib.ptr(g[self.rhn_lo:]), None,
+                                     self.rhn_hi - self.rhn_lo, h.rhn_lr, h.rhn_wd, 0.0, first, _lib.ptr(self.sumsq),
+                                     h.clip, st), "sgd_step")
+        _lib.LAUNCHES += 4
+        self.first_sgd = False
+        return loss.detach(), raw.detach(), logits.detach()
+
+    def step(self, x_train, y_train, x_valid, y_valid):
+        la = self.alpha_step(x_valid, y_valid)
+        lw, raw, logits = self.weight_step(x_train, y_train)
+        return la, lw, raw, logits
+
+
+def train(train_queue, valid_queue, model, rhn, conv, criterion, optimizer, optimizer_a, architect, unrolled, lr,
+          epoch, num_steps, clip_params, report_freq, beta, one_clip=True, train_arch=True, pdarts=True, task=None):
+    """Drop-in for generalNAS_tools/train_and_validate.py:train with torch optimisers supplied by the driver.
+    Returns (labels, predictions, mean loss) like the reference."""
+    import numpy as np
+    dev = next(model.parameters()).device
+    labels, predictions, total, count = [], [], 0.0, 0
+    valid_iter = None
+    for step, (inp, target) in enumerate(train_queue):
+        if step > num_steps:
+            break
+        model.train()
+        inp, target = inp.float().to(dev), target.to(dev)
+        bsz = inp.size(0)
+        hidden = model.init_hidden(bsz)
+        if train_arch:
+            try:
+                inp_s, tgt_s = next(valid_iter)
+            except (StopIteration, TypeError):
+                valid_iter = iter(valid_queue)
+                inp_s, tgt_s = next(valid_iter)
+            inp_s, tgt_s = inp_s.float().to(dev), tgt_s.to(dev)
+            if pdarts:
+                optimizer_a.zero_grad()
+                logits, hidden, _, _ = model(inp_s, hidden, return_h=True)
+                criterion(logits, tgt_s).backward()
+                torch.nn.utils.clip_grad_norm_(model.arch_parameters(), clip_params[2])
+                optimizer_a.step()
+            else:
+                architect.step(hidden, inp, target, model.init_hidden(bsz), inp_s, tgt_s, optimizer, unrolled)
+        optimizer.zero_grad()
+        hidden = model.init_hidden(bsz)
+        logits, hidden, rnn_hs, _ = model(inp, hidden, return_h=True)
+        raw_loss = criterion(logits, target)
+        loss = raw_loss + sum(tar_loss(h, beta) for h in rnn_hs[-1:])
+        loss.backward()
+        if one_clip:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), clip_params[2])
+        else:
+            torch.nn.utils.clip_grad_norm_(conv, clip_params[0])
+            torch.nn.utils.clip_grad_norm_(rhn, clip_params[1])
+        optimizer.step()
+        total += float(loss.detach()) * bsz
+        count += bsz
+        labels.append(target.detach().cpu().numpy())
+        out = torch.softmax(logits, -1) if task == "next_character_prediction" else logits
+        predictions.append(out.detach().cpu().numpy())
+    return labels, predictions, np.float32(total / max(count, 1))

@@ -1,0 +1,190 @@
+"""Whole-supernet parity (tiny configuration on both backends; the B=64 / 4x1000 / 919-label configuration
+on the GPU) against runs of the unmodified reference: logits, loss, every gradient tensor, and one full
+search step through the reference's own train()/Architect/SGD/Adam (tests/golden/model_*.pt)."""
+import math
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import genomenas_oracle as O
+from conftest import GOLDEN, relerr
+
+import genome_nas_b200 as G
+import genome_nas_b200.rnn as R
+
+
+def load(tag):
+    return torch.load(os.path.join(GOLDEN, f"model_{tag}.pt"), weights_only=False)
+
+
+def build(g, device):
+    cfg = g["cfg"]
+    P = O.synthetic_params(g["shapes"], g["seed_params"])
+    mk = lambda k: torch.nn.Parameter(P[k].clone())
+    m = G.RNNModelSearch(cfg.seq_len, cfg.dropouth, cfg.dropoutx, cfg.C, cfg.num_classes, cfg.layers, cfg.steps,
+                         cfg.multiplier, cfg.stem_multiplier, True, 0.2, None, cfg.task, cfg.switches_normal,
+                         cfg.switches_reduce, cfg.switches_rnn, cfg.p_skip, mk("alphas_normal"), mk("alphas_reduce"),
+                         mk("weights"))
+    assert list(m.state_dict().keys()) == list(g["shapes"].keys())
+    assert [tuple(v.shape) for v in m.state_dict().values()] == [tuple(s) for s, _ in g["shapes"].values()]
+    m.load_state_dict(P)
+    m.dropout_lin.p = 0.0
+    return m.to(device).train(), P
+
+
+def probe_vec(i, n):
+    return torch.randn(n, generator=torch.Generator().manual_seed(1000 + i), dtype=torch.float64)
+
+
+def check_forward_backward(g, device, monkeypatch):
+    cfg = g["cfg"]
+    m, _ = build(g, device)
+    masks = [g["xm"], g["hm"]]
+    monkeypatch.setattr(R, "mask2d", lambda B, D, keep, dev: masks.pop(0).to(dev))
+    xt, yt = O.synthetic_batch(g["B"], cfg.seq_len, cfg.num_classes, 0)
+    xt, yt = xt.to(device), yt.to(device)
+    logits, hidden, rnn_hs, _ = m(xt, m.init_hidden(g["B"]), return_h=True)
+    raw = F.binary_cross_entropy(logits, yt)
+    loss = raw + O.Hyper().beta * (rnn_hs[-1][1:] - rnn_hs[-1][:-1]).pow(2).mean()
+    # north star: logits and losses within 1e-3 relative of the reference
+    assert relerr(logits, g["logits64"]) < 1e-4
+    assert abs(float(loss) - float(g["loss64"])) < 1e-5 * abs(float(g["loss64"]))
+    assert abs(float(raw) - float(g["raw64"])) < 1e-5 * abs(float(g["raw64"]))
+    loss.backward()
+    gn, r32 = g["grad_norm64"], g["ref32_err"]
+    total = math.sqrt(sum(v * v for v in gn.values()))
+    names = [n for n, _ in m.named_parameters()]
+    assert names == list(gn.keys())
+    for i, (n, p) in enumerate(m.named_parameters()):
+        ref = gn[n]
+        if ref < 1e-12 * total:
+            continue
+        # per-tensor rel-L2 against fp64 graded like the reference's own fp32 run
+        lim = max(1e-3, 1.5 * r32[n])
+        if n in g["grad64"]:
+            assert relerr(p.grad, g["grad64"][n]) < lim, n
+        else:
+            gd = p.grad.detach().double().cpu()
+            assert abs(float(gd.norm()) - ref) < lim * ref, n
+            dot = float((gd.flatten() * probe_vec(i, gd.numel())).sum())
+            # <g, r> with r ~ N(0, I): |error| <~ ||g - g_ref|| up to a chi-distributed factor
+            assert abs(dot - g["grad_dot64"][n]) < 5 * lim * ref, n
+    dg = dict(m.named_parameters())["decoder.weight"].grad.detach().double().cpu()
+    assert relerr(dg @ g["decoder_proj_vec"].double(), g["decoder_grad_proj64"]) < 2e-3
+    return m
+
+
+@pytest.mark.parametrize("tag", ["tiny", "tiny_pruned"])
+def test_supernet_forward_backward(backend, tag, monkeypatch):
+    check_forward_backward(load(tag), backend, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_supernet_full_size_forward_backward(monkeypatch):
+    """BASELINE config 2: batch 64, one-hot 4x1000, 919 labels, full supernet (38.0 M parameters)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from genome_nas_b200 import _lib
+    _lib._use_library_for_tests(None, "cuda")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    check_forward_backward(load("full"), torch.device("cuda:0"), monkeypatch)
+
+
+def _args():
+    return SimpleNamespace(wdecay=5e-7, clip=0.25, arch_lr=3e-3, arch_wdecay=1e-3)
+
+
+def _check_step_state(m, g, tol_scale=1.0):
+    sd = m.state_dict()
+    for n, ref in g["step_alphas"].items():
+        assert relerr(sd[n], ref) < 2e-5 * tol_scale, n
+    for n, ref in g["step_sample"].items():
+        assert relerr(sd[n], ref) < 5e-4 * tol_scale, n
+    for n, ref in g["step_state_norm"].items():
+        assert abs(float(sd[n].double().norm()) - ref) <= 5e-4 * tol_scale * max(ref, 1e-6), n
+    T = m.decoder.in_features // m.nhid
+    for n, v in sd.items():
+        if n.endswith("num_batches_tracked"):      # two training forwards (valid batch + train batch)
+            assert int(v) == (2 * 9 * T if n == "rnns.0.bn.num_batches_tracked" else 2), n
+
+
+@pytest.mark.parametrize("tag", ["tiny", "tiny_pruned"])
+def test_search_step_reference_loop(backend, tag, monkeypatch):
+    """The reference's loop body (train() + Architect + torch.optim.SGD/Adam) running on the fused modules."""
+    g = load(tag)
+    cfg, hyper = g["cfg"], O.Hyper()
+    m, _ = build(g, backend)
+    mv, mt = g["step_masks"]
+    masks = [mv[0], mv[1], mt[0], mt[1]]
+    monkeypatch.setattr(R, "mask2d", lambda B, D, keep, dev: masks.pop(0).to(dev))
+    xt, yt = O.synthetic_batch(g["B"], cfg.seq_len, cfg.num_classes, 0)
+    xv, yv = O.synthetic_batch(g["B"], cfg.seq_len, cfg.num_classes, 1)
+    conv, rhn = [], []
+    for name, p in m.named_parameters():
+        (rhn if "rnns" in name else conv).append(p)
+    opt = torch.optim.SGD([{"params": conv}, {"params": rhn}], lr=hyper.cnn_lr, weight_decay=hyper.cnn_wd)
+    opt.param_groups[0]["momentum"] = hyper.momentum
+    opt.param_groups[1]["lr"] = hyper.rhn_lr
+    opt.param_groups[1]["weight_decay"] = hyper.rhn_wd
+    arch = G.Architect(m, torch.nn.BCELoss(), _args())
+    labels, preds, avg = G.train([(xt, yt)], [(xv, yv)], m, rhn, conv, torch.nn.BCELoss(), opt, None, arch, False,
+                                 hyper.cnn_lr, 0, 0, [5, 0.25, hyper.clip], 1000, hyper.beta, True, True, False,
+                                 cfg.task)
+    assert abs(float(avg) - float(g["step_loss_train"])) < 1e-4 * abs(float(g["step_loss_train"]))
+    assert preds[0].shape == (g["B"], cfg.num_classes)
+    _check_step_state(m, g)
+
+
+@pytest.mark.parametrize("tag", ["tiny"])
+def test_search_step_fused_optimisers(backend, tag, monkeypatch):
+    """SearchStep: same step with gnas_adam_step / gnas_grad_sumsq / gnas_sgd_step on the flat buffers."""
+    g = load(tag)
+    cfg = g["cfg"]
+    m, _ = build(g, backend)
+    mv, mt = g["step_masks"]
+    masks = [mv[0], mv[1], mt[0], mt[1]]
+    monkeypatch.setattr(R, "mask2d", lambda B, D, keep, dev: masks.pop(0).to(dev))
+    xt, yt = O.synthetic_batch(g["B"], cfg.seq_len, cfg.num_classes, 0)
+    xv, yv = O.synthetic_batch(g["B"], cfg.seq_len, cfg.num_classes, 1)
+    stepper = G.SearchStep(m)
+    la, lw, raw, logits = stepper.step(xt.to(backend), yt.to(backend), xv.to(backend), yv.to(backend))
+    assert abs(float(la) - float(g["step_loss_valid"])) < 1e-4 * abs(float(g["step_loss_valid"]))
+    assert abs(float(lw) - float(g["step_loss_train"])) < 1e-4 * abs(float(g["step_loss_train"]))
+    _check_step_state(m, g)
+
+
+def test_seeded_construction_matches_reference_initialisation():
+    """Same constructor calls in the same order as the reference => identical initial weights for a seed.
+    Known answer from SURVEY.md 8(c): sum |params| = 800971.928 for seed 3 on the full supernet."""
+    import numpy as np
+    torch.manual_seed(3)
+    np.random.seed(3)
+    a = [torch.nn.Parameter(torch.FloatTensor(1e-3 * np.random.randn(*s))) for s in ((14, 9), (14, 9), (36, 5))]
+    sw = lambda n, k: [[True] * k for _ in range(n)]
+    m = G.RNNModelSearch(1000, 0.0, 0.0, 8, 919, 6, 4, 4, 3, True, 0.2, None, 'TF_bindings', sw(14, 9), sw(14, 9),
+                         sw(36, 5), 0.0, *a)
+    assert sum(p.numel() for p in m.parameters()) == 38035471
+    assert len(m.state_dict()) == 3933
+    total = sum(float(p.detach().double().abs().sum()) for p in m.parameters())
+    assert abs(total - 800971.928) < 0.05
+    assert torch.allclose(m.alphas_normal[0, :3].detach(), torch.tensor([1.78863e-3, 4.36510e-4, 9.64975e-5]), rtol=1e-4)
+
+
+def test_genotype_and_api_surface():
+    g = load("tiny")
+    m, _ = build(g, torch.device("cpu"))
+    geno = m.genotype()
+    assert len(geno.normal) == 8 and len(geno.reduce) == 8 and len(geno.rnn) == 8
+    assert all(op != "none" for op, _ in geno.normal + geno.reduce + geno.rnn)
+    assert list(geno.normal_concat) == [2, 3, 4, 5] and list(geno.rnn_concat) == list(range(1, 9))
+    assert [p.data_ptr() for p in m.arch_parameters()] == [m.alphas_normal.data_ptr(), m.alphas_reduce.data_ptr(),
+                                                           m.weights.data_ptr()]
+    assert m.rnns[0].weights is m.weights
+    new = m.new()
+    assert all(torch.equal(a, b) for a, b in zip(new.arch_parameters(), m.arch_parameters()))
+    h = m.init_hidden(5)
+    assert len(h) == 1 and tuple(h[0].shape) == (1, 5, m.nhid)
