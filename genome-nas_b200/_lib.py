@@ -34,6 +34,9 @@ _I64P = C.POINTER(C.c_int64)
 _SIGS = {
     "gnas_version": (C.c_int, []),
     "gnas_last_error": (C.c_char_p, []),
+    "gnas_kernel_launches": (C.c_int64, []),
+    "gnas_profile_enable": (C.c_int, [C.c_int]),
+    "gnas_profile_report": (C.c_int64, [C.c_char_p, C.c_int64]),
     "gnas_cell_workspace": (C.c_int, [C.POINTER(CellDesc), _I64P, _I64P]),
     "gnas_cell_forward": (C.c_int, [C.POINTER(CellDesc), _P, _P, _P, _P, _P, _I64P, _P, _P, _P]),
     "gnas_cell_backward": (C.c_int, [C.POINTER(CellDesc), _P, _P, _P, _P, _P, _I64P, _P, _P, _P, _P, _P, _P, _P,
@@ -86,6 +89,26 @@ def _use_library_for_tests(path, device_type):
     global _lib, _device_type
     _lib = _bind(path) if path else None
     _device_type = device_type
+
+
+def kernel_launches():
+    return int(lib().gnas_kernel_launches())
+
+
+def profile(enable):
+    lib().gnas_profile_enable(1 if enable else 0)
+
+
+def profile_report():
+    """{kernel name: (launches, total device ms)} recorded since profile(True)."""
+    buf = C.create_string_buffer(1 << 20)
+    n = lib().gnas_profile_report(buf, len(buf))
+    out = {}
+    if n > 0:
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit("\t", 2)
+            out[name] = (int(cnt), float(ms))
+    return out
 
 
 def check(rc, what=""):

@@ -2,10 +2,20 @@
 #pragma once
 #ifdef GNAS_EMUL
 // tests/emul/cuda_emul.h is force-included by the emulator build (test infrastructure only)
-#define GNAS_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  emul::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); }, false)
-#define GNAS_LAUNCH_COOP(kernel, grid, block, smem, stream, ...) \
-  emul::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); }, true)
+namespace gnas {
+void prof_before(const char* kernel, const char* where, cudaStream_t stream);
+void prof_after(cudaStream_t stream);
+}
+#define GNAS_LAUNCH(kernel, grid, block, smem, stream, ...)                   \
+  do {                                                                        \
+    gnas::prof_before(#kernel, __PRETTY_FUNCTION__, stream);                  \
+    emul::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); }, false);   \
+  } while (0)
+#define GNAS_LAUNCH_COOP(kernel, grid, block, smem, stream, ...)              \
+  do {                                                                        \
+    gnas::prof_before(#kernel, __PRETTY_FUNCTION__, stream);                  \
+    emul::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); }, true);    \
+  } while (0)
 #define GNAS_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emul::cur_block()->dyn_smem)
 #define GNAS_SET_SMEM(kernel, bytes) 0
 #define GNAS_SPIN_PAUSE() GNAS_EMUL_YIELD()
@@ -15,8 +25,16 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
-#define GNAS_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+namespace gnas {
+void prof_before(const char* kernel, const char* where, cudaStream_t stream);
+void prof_after(cudaStream_t stream);
+}
+#define GNAS_LAUNCH(kernel, grid, block, smem, stream, ...)          \
+  do {                                                               \
+    gnas::prof_before(#kernel, __PRETTY_FUNCTION__, stream);         \
+    kernel<<<grid, block, smem, stream>>>(__VA_ARGS__);              \
+    gnas::prof_after(stream);                                        \
+  } while (0)
 #define GNAS_DYN_SMEM(T, name)                                       \
   extern __shared__ __align__(16) unsigned char gnas_dyn_smem_raw[]; \
   T* name = reinterpret_cast<T*>(gnas_dyn_smem_raw)

@@ -741,7 +741,9 @@ extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const floa
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rhn_forward, kThreads, smem);
     if (per_sm * nsm < grid) { set_error("rhn_forward: grid does not fit co-resident (hidden size too large)"); return GNAS_ERR_UNSUPPORTED; }
     void* args[] = {(void*)&f};
+    prof_before("k_rhn_forward", "", st);
     cudaError_t e = cudaLaunchCooperativeKernel((void*)k_rhn_forward, dim3(grid), dim3(kThreads), args, smem, st);
+    prof_after(st);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
   }
 #endif

@@ -36,6 +36,13 @@ enum { GNAS_NONE = 0, GNAS_MAX_POOL = 1, GNAS_AVG_POOL = 2, GNAS_SKIP = 3, GNAS_
 
 int gnas_version(void);
 const char* gnas_last_error(void);
+/* number of kernels this library has launched in this process (monotonic) */
+int64_t gnas_kernel_launches(void);
+/* per-kernel device timing for bench.py: while enabled every launch is bracketed by CUDA events on its
+ * stream; gnas_profile_report synchronises, writes "kernel<TAB>count<TAB>total_ms" lines into buf
+ * (returns bytes written, <0 if cap is too small) and clears the records. */
+int gnas_profile_enable(int on);
+int64_t gnas_profile_report(char* buf_host, int64_t cap);
 
 /* ---- CNN search cell: darts_tools/model_discCNN.py:96-201 (CNN_Cell_search) with its
  * MixedOps (:46-93) and the operator zoo generalNAS_tools/operations_14_9.py:17-300.
