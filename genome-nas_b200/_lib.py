@@ -51,7 +51,7 @@ _SIGS = {
     "gnas_grad_sumsq": (C.c_int, [_P, C.c_int64, _P, _P]),
     "gnas_sgd_step": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P, C.c_float, _P]),
     "gnas_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                 C.c_int, _P]),
+                                 C.c_int, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -258,26 +258,29 @@ struct WgJob {
   float* dw;                         // [Cout][Cin][KW], accumulated with atomics
   int Cin, Lo, Lin, tin;
 };
-struct WgBatch { int n, B, Cout, S, pad, BCH, TL, COB, CIB, G; WgJob j[kMaxDense]; };
+struct WgBatch { int n, B, Cout, S, pad, TPC, TL, COB, CIB, G; WgJob j[kMaxDense]; };
+
+// Position tiles are enumerated b-major: tile -> (b, l0).  A CTA owns TPC consecutive tiles (blockIdx.y),
+// one block of the weight matrix (blockIdx.x) of one job (blockIdx.z), accumulates in registers and
+// flushes once with atomics into the flat gradient buffer.
 
 // dW[co,ci] += sum_{b,l} dz[b,co,l] * T(r)[b,ci,l*S]
 template <int TC>
 __global__ void __launch_bounds__(kThreads) k_pw_wgrad(const __grid_constant__ WgBatch P) {
   const WgJob& J = P.j[blockIdx.z];
-  const int nbo = (P.Cout + P.COB - 1) / P.COB, nbi = (J.Cin + P.CIB - 1) / P.CIB;
+  const int nbi = (J.Cin + P.CIB - 1) / P.CIB;
   const int wb = blockIdx.x;
-  if (wb >= nbo * nbi) return;
   const int co0 = (wb / nbi) * P.COB, ci0 = (wb % nbi) * P.CIB;
-  const int cob = min(P.COB, P.Cout - co0), cib = min(P.CIB, J.Cin - ci0);
-  const int nco_t = cob / TC, nci_t = cib / TC;
-  const int tid = threadIdx.x;
-  const int per = nco_t * nci_t;
+  const int cob = P.COB, cib = P.CIB;
+  const int nci_t = cib / TC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (cob / TC) * nci_t;
   const int G = kThreads / per;
   const int grp = tid / per, r2 = tid - grp * per;
   const int cq = r2 / nci_t, iq = r2 - cq * nci_t;
   const bool active = grp < G;
   const int TL = P.TL;
-  const int po = P.COB + 4, pi = P.CIB + 4;
+  const int po = cob + 4, pi = cib + 4;
   GNAS_DYN_SMEM(float, smem);
   float* dzs = smem;             // [TL][po]
   float* rs = dzs + TL * po;     // [TL][pi]
@@ -286,47 +289,53 @@ __global__ void __launch_bounds__(kThreads) k_pw_wgrad(const __grid_constant__ W
   for (int i = 0; i < TC; ++i)
 #pragma unroll
     for (int k = 0; k < TC; ++k) acc[i][k] = 0.f;
-  const int b0 = blockIdx.y * P.BCH, b1 = min(P.B, b0 + P.BCH);
-  for (int b = b0; b < b1; ++b) {
-    for (int l0 = 0; l0 < J.Lo; l0 += TL) {
-      const int nl = min(TL, J.Lo - l0);
-      for (int i = tid; i < cob * TL; i += kThreads) {
-        const int c = i / TL, l = i - c * TL;
-        float v = 0.f;
-        if (l < nl) {
-          const long long o = (long long)(co0 + c) * J.Lo + l0 + l;
-          const float gv = J.g[(long long)b * J.gbs + o];
-          v = J.z ? fmaf(J.coef[co0 + c], gv, fmaf(J.coef[P.Cout + co0 + c], J.z[(long long)b * J.zbs + o], J.coef[2 * P.Cout + co0 + c])) : gv;
-        }
-        dzs[l * po + c] = v;
+  const int ntl = (J.Lo + TL - 1) / TL;
+  const int tile_end = min(P.B * ntl, (int)(blockIdx.y + 1) * P.TPC);
+  for (int tile = blockIdx.y * P.TPC; tile < tile_end; ++tile) {
+    const int b = tile / ntl, l0 = (tile - b * ntl) * TL;
+    const int nl = min(TL, J.Lo - l0);
+    for (int c = warp; c < cob; c += kThreads / 32) {
+      const long long o = (long long)b * J.gbs + (long long)(co0 + c) * J.Lo + l0;
+      const float* gr = J.g + o;
+      if (J.z) {
+        const float* zr = J.z + (long long)b * J.zbs + (long long)(co0 + c) * J.Lo + l0;
+        const float A = J.coef[co0 + c], Bz = J.coef[P.Cout + co0 + c], D = J.coef[2 * P.Cout + co0 + c];
+        for (int l = lane; l < TL; l += 32) dzs[l * po + c] = l < nl ? fmaf(A, gr[l], fmaf(Bz, zr[l], D)) : 0.f;
+      } else {
+        for (int l = lane; l < TL; l += 32) dzs[l * po + c] = l < nl ? gr[l] : 0.f;
       }
-      for (int i = tid; i < cib * TL; i += kThreads) {
-        const int c = i / TL, l = i - c * TL;
-        float v = 0.f;
-        if (l < nl) {
-          const int pos = (l0 + l) * P.S;
-          float mean = 0.f, rstd = 1.f;
-          if (J.tin >= T_BN_RELU) { mean = J.r_stat[ci0 + c]; rstd = J.r_stat[J.Cin + ci0 + c]; }
-          v = apply_tin(J.r[(long long)b * J.rbs + (long long)(ci0 + c) * J.Lin + pos], J.tin, mean, rstd);
-        }
-        rs[l * pi + c] = v;
-      }
-      __syncthreads();
-      if (active) {
-        for (int l = grp; l < nl; l += G) {
-          float a[TC], bb[TC];
-#pragma unroll
-          for (int i = 0; i < TC; ++i) a[i] = dzs[l * po + cq * TC + i];
-#pragma unroll
-          for (int k = 0; k < TC; ++k) bb[k] = rs[l * pi + iq * TC + k];
-#pragma unroll
-          for (int i = 0; i < TC; ++i)
-#pragma unroll
-            for (int k = 0; k < TC; ++k) acc[i][k] = fmaf(a[i], bb[k], acc[i][k]);
-        }
-      }
-      __syncthreads();
     }
+    for (int c = warp; c < cib; c += kThreads / 32) {
+      const float* rr = J.r + (long long)b * J.rbs + (long long)(ci0 + c) * J.Lin + (long long)l0 * P.S;
+      float mean = 0.f, rstd = 1.f;
+      if (J.tin >= T_BN_RELU) { mean = J.r_stat[ci0 + c]; rstd = J.r_stat[J.Cin + ci0 + c]; }
+      for (int l = lane; l < TL; l += 32) rs[l * pi + c] = l < nl ? apply_tin(rr[l * P.S], J.tin, mean, rstd) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      const float* dp = dzs + cq * TC;
+      const float* rp = rs + iq * TC;
+      for (int l = grp; l < nl; l += G) {
+        float a[TC], bb[TC];
+        if (TC >= 4) {
+#pragma unroll
+          for (int i = 0; i < TC; i += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(dp + l * po + i);
+            a[i] = v.x; a[i + 1 < TC ? i + 1 : 0] = v.y; a[i + 2 < TC ? i + 2 : 0] = v.z; a[i + 3 < TC ? i + 3 : 0] = v.w;
+            const float4 u = *reinterpret_cast<const float4*>(rp + l * pi + i);
+            bb[i] = u.x; bb[i + 1 < TC ? i + 1 : 0] = u.y; bb[i + 2 < TC ? i + 2 : 0] = u.z; bb[i + 3 < TC ? i + 3 : 0] = u.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < TC; ++i) { a[i] = dp[l * po + i]; bb[i] = rp[l * pi + i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < TC; ++i)
+#pragma unroll
+          for (int k = 0; k < TC; ++k) acc[i][k] = fmaf(a[i], bb[k], acc[i][k]);
+      }
+    }
+    __syncthreads();
   }
   if (active) {
 #pragma unroll
@@ -341,75 +350,72 @@ __global__ void __launch_bounds__(kThreads) k_pw_wgrad(const __grid_constant__ W
 template <int KW, int S>
 __global__ void __launch_bounds__(kThreads) k_conv_wgrad(const __grid_constant__ WgBatch P) {
   const WgJob& J = P.j[blockIdx.z];
-  const int nbo = (P.Cout + P.COB - 1) / P.COB, nbi = (J.Cin + P.CIB - 1) / P.CIB;
+  const int nbi = (J.Cin + P.CIB - 1) / P.CIB;
   const int wb = blockIdx.x;
-  if (wb >= nbo * nbi) return;
   const int co0 = (wb / nbi) * P.COB, ci0 = (wb % nbi) * P.CIB;
-  const int cob = min(P.COB, P.Cout - co0), cib = min(P.CIB, J.Cin - ci0);
+  const int cob = P.COB, cib = P.CIB;
   const int ncoq = cob / 4;
   const int per = ncoq * cib;
   const int G = kThreads / per;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = tid / per, r2 = tid - grp * per;
   const int coq = r2 / cib, ci = r2 - coq * cib;
   const bool active = grp < G;
-  const int TLg = P.TL;                 // positions per group per iteration
-  const int TLc = TLg * G;              // positions per CTA iteration
+  const int TLg = P.TL;                 // positions per group per tile
+  const int TLc = TLg * G;              // positions per tile
   const int pz = TLc | 1;
   const int Wr = (TLc - 1) * S + KW;
   const int pr = Wr | 1;
   GNAS_DYN_SMEM(float, smem);
   float* dzs = smem;                    // [cob][pz]
-  float* rs = dzs + P.COB * pz;         // [cib][pr]
+  float* rs = dzs + cob * pz;           // [cib][pr]
   float acc[4][KW];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int t = 0; t < KW; ++t) acc[i][t] = 0.f;
-  const int b0 = blockIdx.y * P.BCH, b1 = min(P.B, b0 + P.BCH);
-  for (int b = b0; b < b1; ++b) {
-    for (int l0 = 0; l0 < J.Lo; l0 += TLc) {
-      const int nl = min(TLc, J.Lo - l0);
-      for (int i = tid; i < cob * TLc; i += kThreads) {
-        const int c = i / TLc, l = i - c * TLc;
-        float v = 0.f;
-        if (l < nl) {
-          const long long o = (long long)(co0 + c) * J.Lo + l0 + l;
-          const float gv = J.g[(long long)b * J.gbs + o];
-          v = J.z ? fmaf(J.coef[co0 + c], gv, fmaf(J.coef[P.Cout + co0 + c], J.z[(long long)b * J.zbs + o], J.coef[2 * P.Cout + co0 + c])) : gv;
-        }
-        dzs[c * pz + l] = v;
+  const int ntl = (J.Lo + TLc - 1) / TLc;
+  const int tile_end = min(P.B * ntl, (int)(blockIdx.y + 1) * P.TPC);
+  for (int tile = blockIdx.y * P.TPC; tile < tile_end; ++tile) {
+    const int b = tile / ntl, l0 = (tile - b * ntl) * TLc;
+    const int nl = min(TLc, J.Lo - l0);
+    for (int c = warp; c < cob; c += kThreads / 32) {
+      const float* gr = J.g + (long long)b * J.gbs + (long long)(co0 + c) * J.Lo + l0;
+      if (J.z) {
+        const float* zr = J.z + (long long)b * J.zbs + (long long)(co0 + c) * J.Lo + l0;
+        const float A = J.coef[co0 + c], Bz = J.coef[P.Cout + co0 + c], D = J.coef[2 * P.Cout + co0 + c];
+        for (int l = lane; l < TLc; l += 32) dzs[c * pz + l] = l < nl ? fmaf(A, gr[l], fmaf(Bz, zr[l], D)) : 0.f;
+      } else {
+        for (int l = lane; l < TLc; l += 32) dzs[c * pz + l] = l < nl ? gr[l] : 0.f;
       }
-      const int in0 = l0 * S - P.pad;
-      for (int i = tid; i < cib * Wr; i += kThreads) {
-        const int c = i / Wr, p = i - c * Wr;
-        const int pos = in0 + p;
-        float v = 0.f;
-        if (pos >= 0 && pos < J.Lin) {
-          float mean = 0.f, rstd = 1.f;
-          if (J.tin >= T_BN_RELU) { mean = J.r_stat[ci0 + c]; rstd = J.r_stat[J.Cin + ci0 + c]; }
-          v = apply_tin(J.r[(long long)b * J.rbs + (long long)(ci0 + c) * J.Lin + pos], J.tin, mean, rstd);
-        }
-        rs[c * pr + p] = v;
-      }
-      __syncthreads();
-      if (active) {
-        const int le = min(nl, (grp + 1) * TLg);
-        const float* rr = rs + ci * pr;
-        for (int l = grp * TLg; l < le; ++l) {
-          float d[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) d[i] = dzs[(coq * 4 + i) * pz + l];
-#pragma unroll
-          for (int t = 0; t < KW; ++t) {
-            const float rv = rr[l * S + t];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i][t] = fmaf(d[i], rv, acc[i][t]);
-          }
-        }
-      }
-      __syncthreads();
     }
+    const int in0 = l0 * S - P.pad;
+    for (int c = warp; c < cib; c += kThreads / 32) {
+      const float* rr = J.r + (long long)b * J.rbs + (long long)(ci0 + c) * J.Lin;
+      float mean = 0.f, rstd = 1.f;
+      if (J.tin >= T_BN_RELU) { mean = J.r_stat[ci0 + c]; rstd = J.r_stat[J.Cin + ci0 + c]; }
+      for (int p = lane; p < Wr; p += 32) {
+        const int pos = in0 + p;
+        rs[c * pr + p] = (pos >= 0 && pos < J.Lin) ? apply_tin(rr[pos], J.tin, mean, rstd) : 0.f;
+      }
+    }
+    __syncthreads();
+    if (active) {
+      const int le = min(nl, (grp + 1) * TLg);
+      const float* rr = rs + ci * pr;
+      const float* dz0 = dzs + (coq * 4) * pz;
+      for (int l = grp * TLg; l < le; ++l) {
+        const float d0 = dz0[l], d1 = dz0[pz + l], d2 = dz0[2 * pz + l], d3 = dz0[3 * pz + l];
+        const float* rl = rr + l * S;
+#pragma unroll
+        for (int t = 0; t < KW; ++t) {
+          const float rv = rl[t];
+          acc[0][t] = fmaf(d0, rv, acc[0][t]); acc[1][t] = fmaf(d1, rv, acc[1][t]);
+          acc[2][t] = fmaf(d2, rv, acc[2][t]); acc[3][t] = fmaf(d3, rv, acc[3][t]);
+        }
+      }
+    }
+    __syncthreads();
   }
   if (active) {
 #pragma unroll

@@ -150,65 +150,77 @@ static inline int pick_tc(int a, int b) {
   if (a % 2 == 0 && b % 2 == 0 && m >= 8) return 2;
   return 1;
 }
+// CTAs per launch to aim for when splitting the position range of a weight-gradient job
+constexpr int kWgradTargetCtas = 4 * 148;
+
 template <int TC>
-static void launch_pw_wgrad_t(WgBatch& b, int maxblocks, cudaStream_t st) {
+static void launch_pw_wgrad_t(WgBatch& b, int nblk, int ny, cudaStream_t st) {
   const size_t smem = sizeof(float) * (size_t)b.TL * (b.COB + 4 + b.CIB + 4);
   GNAS_PREP_SMEM((k_pw_wgrad<TC>), smem);
-  dim3 grid(maxblocks, cdiv(b.B, b.BCH), b.n);
+  dim3 grid(nblk, ny, b.n);
   GNAS_LAUNCH((k_pw_wgrad<TC>), grid, dim3(kThreads), smem, st, b);
 }
-// all jobs of a batch must share Cin (true for every call site)
+// all jobs of a batch must share Cin and Lo (true for every call site)
 static int launch_pw_wgrad(int S, WgBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
-  const int Cin = b.j[0].Cin;
-  for (int i = 1; i < b.n; ++i) if (b.j[i].Cin != Cin) { set_error("pw_wgrad: mixed Cin"); return GNAS_ERR_ARG; }
+  const int Cin = b.j[0].Cin, Lo = b.j[0].Lo;
+  for (int i = 1; i < b.n; ++i) if (b.j[i].Cin != Cin || b.j[i].Lo != Lo) { set_error("pw_wgrad: mixed shapes"); return GNAS_ERR_ARG; }
   const int TC = pick_tc(b.Cout, Cin);
   b.S = S; b.pad = 0;
   b.COB = b.Cout < 16 * TC ? b.Cout : 16 * TC;
   b.CIB = Cin < 16 * TC ? Cin : 16 * TC;
   while ((b.COB / TC) * (b.CIB / TC) > kThreads) b.CIB /= 2;
-  b.TL = 64;
-  b.BCH = b.B >= 32 ? 8 : (b.B >= 8 ? 4 : 1);
-  const int nblk = cdiv(b.Cout, b.COB) * cdiv(Cin, b.CIB);
-  if (b.Cout % b.COB || Cin % b.CIB) { set_error("pw_wgrad: channel counts must tile"); return GNAS_ERR_SHAPE; }
+  if (b.Cout % b.COB || Cin % b.CIB || b.COB % TC || b.CIB % TC) { set_error("pw_wgrad: channel counts must tile"); return GNAS_ERR_SHAPE; }
+  const int cmax = b.COB > b.CIB ? b.COB : b.CIB;
+  int tl = 4096 / cmax;
+  tl = tl > 512 ? 512 : (tl < 64 ? 64 : tl);
+  b.TL = tl;
+  const int nblk = (b.Cout / b.COB) * (Cin / b.CIB);
+  const int tiles = b.B * cdiv(Lo, b.TL);
+  int tpc = (int)((long long)tiles * nblk * b.n / kWgradTargetCtas);
+  b.TPC = tpc < 1 ? 1 : tpc;
+  const int ny = cdiv(tiles, b.TPC);
   switch (TC) {
-    case 8: launch_pw_wgrad_t<8>(b, nblk, st); break;
-    case 4: launch_pw_wgrad_t<4>(b, nblk, st); break;
-    case 2: launch_pw_wgrad_t<2>(b, nblk, st); break;
-    default: launch_pw_wgrad_t<1>(b, nblk, st); break;
+    case 8: launch_pw_wgrad_t<8>(b, nblk, ny, st); break;
+    case 4: launch_pw_wgrad_t<4>(b, nblk, ny, st); break;
+    case 2: launch_pw_wgrad_t<2>(b, nblk, ny, st); break;
+    default: launch_pw_wgrad_t<1>(b, nblk, ny, st); break;
   }
   b.n = 0;
   return 0;
 }
 
 template <int KW, int S>
-static void launch_conv_wgrad_t(WgBatch& b, int nblk, cudaStream_t st) {
+static void launch_conv_wgrad_t(WgBatch& b, int nblk, int Lo, cudaStream_t st) {
   const int per = (b.COB / 4) * b.CIB;
   const int G = kThreads / per;
   int tlg = 512 / G;
   tlg = tlg > 64 ? 64 : (tlg < 16 ? 16 : tlg);
+  while (tlg > 16 && tlg * G >= 2 * Lo) tlg /= 2;     // short rows: do not pad a tile to twice the row
   b.TL = tlg;
   const int TLc = tlg * G;
   const int pz = TLc | 1, pr = ((TLc - 1) * S + KW) | 1;
   const size_t smem = sizeof(float) * ((size_t)b.COB * pz + (size_t)b.CIB * pr);
   GNAS_PREP_SMEM((k_conv_wgrad<KW, S>), smem);
-  dim3 grid(nblk, cdiv(b.B, b.BCH), b.n);
+  const int tiles = b.B * cdiv(Lo, TLc);
+  int tpc = (int)((long long)tiles * nblk * b.n / kWgradTargetCtas);
+  b.TPC = tpc < 1 ? 1 : tpc;
+  dim3 grid(nblk, cdiv(tiles, b.TPC), b.n);
   GNAS_LAUNCH((k_conv_wgrad<KW, S>), grid, dim3(kThreads), smem, st, b);
 }
 static int launch_conv_wgrad(int KW, int S, int pad, WgBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
-  const int Cin = b.j[0].Cin;
-  for (int i = 1; i < b.n; ++i) if (b.j[i].Cin != Cin) { set_error("conv_wgrad: mixed Cin"); return GNAS_ERR_ARG; }
+  const int Cin = b.j[0].Cin, Lo = b.j[0].Lo;
+  for (int i = 1; i < b.n; ++i) if (b.j[i].Cin != Cin || b.j[i].Lo != Lo) { set_error("conv_wgrad: mixed shapes"); return GNAS_ERR_ARG; }
   b.S = S; b.pad = pad;
   b.COB = b.Cout < 32 ? b.Cout : 32;
   b.CIB = Cin < 32 ? Cin : 32;
   if (b.Cout % b.COB || Cin % b.CIB || b.COB % 4) { set_error("conv_wgrad: channel counts must tile"); return GNAS_ERR_SHAPE; }
-  b.BCH = b.B >= 32 ? 8 : (b.B >= 8 ? 4 : 1);
   const int nblk = (b.Cout / b.COB) * (Cin / b.CIB);
-  if (KW == 15 && S == 1) launch_conv_wgrad_t<15, 1>(b, nblk, st);
-  else if (KW == 15 && S == 2) launch_conv_wgrad_t<15, 2>(b, nblk, st);
-  else if (KW == 15 && S == 3) launch_conv_wgrad_t<15, 3>(b, nblk, st);
-  else if (KW == 13 && S == 1) launch_conv_wgrad_t<13, 1>(b, nblk, st);
+  if (KW == 15 && S == 1) launch_conv_wgrad_t<15, 1>(b, nblk, Lo, st);
+  else if (KW == 15 && S == 2) launch_conv_wgrad_t<15, 2>(b, nblk, Lo, st);
+  else if (KW == 15 && S == 3) launch_conv_wgrad_t<15, 3>(b, nblk, Lo, st);
+  else if (KW == 13 && S == 1) launch_conv_wgrad_t<13, 1>(b, nblk, Lo, st);
   else { set_error("conv_wgrad: unsupported (KW, stride)"); return GNAS_ERR_UNSUPPORTED; }
   b.n = 0;
   return 0;

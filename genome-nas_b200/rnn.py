@@ -126,7 +126,10 @@ class DARTSCellSearch(nn.Module):
 
     def forward(self, inputs, hidden):
         T, B = inputs.size(0), inputs.size(1)
-        if self.training:
+        provider = self.__dict__.get("_mask_provider")   # SearchStep's CUDA-graph mode feeds static mask buffers
+        if self.training and provider is not None:
+            x_mask, h_mask = provider(B, inputs.size(2))
+        elif self.training:
             x_mask = mask2d(B, inputs.size(2), 1. - self.dropoutx, inputs.device)
             h_mask = mask2d(B, hidden.size(2), 1. - self.dropouth, inputs.device)
         else:

@@ -51,8 +51,8 @@ class SearchStep:
         self.adam_m = torch.zeros(self.n_alpha, dtype=torch.float32, device=dev)
         self.adam_v = torch.zeros(self.n_alpha, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
-        self.t_adam = 0
-        self.first_sgd = True
+        self.t_adam = torch.zeros(1, dtype=torch.int32, device=dev)     # device-side so CUDA graphs stay valid
+        self.graph = None
 
     def _refresh(self):
         r = self.model.flat_region()
@@ -76,30 +76,44 @@ class SearchStep:
         if self.world > 1:
             torch.distributed.all_reduce(ga, group=self.pg)
             ga.div_(self.world)
-        self.t_adam += 1
         _lib.check(lib.gnas_adam_step(_lib.ptr(flat), _lib.ptr(ga), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v),
                                       self.n_alpha, h.arch_lr, h.arch_wd, h.adam_betas[0], h.adam_betas[1], h.adam_eps,
-                                      self.t_adam, _lib.stream_ptr(flat)), "adam_step")
+                                      0, _lib.ptr(self.t_adam), _lib.stream_ptr(flat)), "adam_step")
         _lib.LAUNCHES += 1
         return loss.detach()
 
-    def weight_step(self, x_train, y_train):
-        lib, h = _lib.lib(), self.h
+    def weight_backward(self, x_train, y_train, zero=True):
+        """fwd + bwd of BCE + beta*TAR on a training batch; gradients land in the flat buffer."""
         flat, g = self._refresh()
         model = self.model
-        g.zero_()
+        if zero:
+            g.zero_()
         logits, hidden, rnn_hs, _ = model(x_train, model.init_hidden(x_train.size(0)), return_h=True)
         raw = F.binary_cross_entropy(logits, y_train)
-        loss = raw + tar_loss(rnn_hs[-1], h.beta)
+        loss = raw + tar_loss(rnn_hs[-1], self.h.beta)
         loss.backward()
+        return loss.detach(), raw.detach(), logits.detach()
+
+    def reduce_gradients(self, scale=None):
+        """batch-sharded data parallelism: mean of the per-rank gradients (one NCCL allreduce of 152 MB)."""
+        flat, g = self._refresh()
         if self.world > 1:
             torch.distributed.all_reduce(g, group=self.pg)
             g.div_(self.world)
+        elif scale is not None:
+            g.mul_(scale)
+
+    def apply_weight_update(self):
+        """global-norm clip (train_and_validate.py:146-147) + SGD over both parameter groups
+        (train_genomicDARTS.py:258-276: 'rnns' -> lr rhn_lr, no momentum; everything else, alphas included,
+        lr cnn_lr with momentum)."""
+        lib, h = _lib.lib(), self.h
+        flat, g = self._refresh()
         st = _lib.stream_ptr(flat)
         self.sumsq.zero_()
         _lib.check(lib.gnas_grad_sumsq(_lib.ptr(g), self.total, _lib.ptr(self.sumsq), st), "grad_sumsq")
-        first = 1 if self.first_sgd else 0
-        for lo, hi in ((0, self.rhn_lo), (self.rhn_hi, self.total)):      # "conv" group: everything but rnns.*
+        first = 0     # momentum buffers start at zero: momentum*0 + d == d, torch's first-step rule
+        for lo, hi in ((0, self.rhn_lo), (self.rhn_hi, self.total)):
             _lib.check(lib.gnas_sgd_step(_lib.ptr(flat[lo:]), _lib.ptr(g[lo:]), _lib.ptr(self.mom[lo:]), hi - lo,
                                          h.cnn_lr, h.cnn_wd, h.momentum, first, _lib.ptr(self.sumsq), h.clip, st),
                        "sgd_step")
@@ -107,13 +121,76 @@ class SearchStep:
                                      self.rhn_hi - self.rhn_lo, h.rhn_lr, h.rhn_wd, 0.0, first, _lib.ptr(self.sumsq),
                                      h.clip, st), "sgd_step")
         _lib.LAUNCHES += 4
-        self.first_sgd = False
-        return loss.detach(), raw.detach(), logits.detach()
 
-    def step(self, x_train, y_train, x_valid, y_valid):
+    def weight_step(self, x_train, y_train):
+        out = self.weight_backward(x_train, y_train)
+        self.reduce_gradients()
+        self.apply_weight_update()
+        return out
+
+    def _step_eager(self, x_train, y_train, x_valid, y_valid):
         la = self.alpha_step(x_valid, y_valid)
         lw, raw, logits = self.weight_step(x_train, y_train)
         return la, lw, raw, logits
+
+    def step(self, x_train, y_train, x_valid, y_valid):
+        if self.graph is None:
+            return self._step_eager(x_train, y_train, x_valid, y_valid)
+        for dst, src in zip(self._static_in, (x_train, y_train, x_valid, y_valid)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._draw_static_masks()
+        self.graph.replay()
+        return self._static_out
+
+    # ---- CUDA-graph mode: the ~3.7 k launches of a step are replayed from one captured graph --------------
+    def _draw_static_masks(self):
+        """Same CPU random stream as the eager path: x mask then h mask for the validation pass, then again
+        for the training pass (utils.py:354-363 draws on the CPU generator)."""
+        rnn = self.model.rnns[0]
+        B, H = self._static_masks[0].shape
+        for i, keep in enumerate((1. - rnn.dropoutx, 1. - rnn.dropouth) * 2):
+            self._mask_host[i].copy_(torch.floor(torch.rand(B, H) + keep) / keep)
+            self._static_masks[i].copy_(self._mask_host[i], non_blocking=True)
+
+    def capture(self, x_train, y_train, x_valid, y_valid, warmup=2):
+        """Capture alpha step + weight step into one CUDA graph.  `warmup` real steps run first on a side
+        stream (they are ordinary optimisation steps on the given batch)."""
+        dev = x_train.device
+        rnn = self.model.rnns[0]
+        B, H = x_train.size(0), rnn.nhid
+        self._static_in = [t.clone() for t in (x_train, y_train, x_valid, y_valid)]
+        self._static_masks = [torch.ones(B, H, device=dev) for _ in range(4)]
+        self._mask_host = [torch.ones(B, H).pin_memory() for _ in range(4)]
+        cursor = [0]
+
+        def provider(b, h):
+            i = cursor[0]
+            cursor[0] = (i + 2) % 4
+            return self._static_masks[i], self._static_masks[i + 1]
+
+        rnn.__dict__["_mask_provider"] = provider
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._draw_static_masks()
+                    self._step_eager(*self._static_in)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            cursor[0] = 0
+            n0 = _lib.kernel_launches()
+            with torch.cuda.graph(graph):
+                self._static_out = self._step_eager(*self._static_in)
+            self.graph_launches = _lib.kernel_launches() - n0      # our kernels inside one replay
+            self.graph = graph
+        except Exception:
+            rnn.__dict__.pop("_mask_provider", None)
+            self.graph = None
+            raise
+        return self
 
 
 def train(train_queue, valid_queue, model, rhn, conv, criterion, optimizer, optimizer_a, architect, unrolled, lr,

@@ -130,8 +130,10 @@ int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const float* h0, con
 int gnas_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
 int gnas_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float wd,
                   float momentum, int first_step, const double* sumsq, float clip, void* stream);
+/* step_dev (optional, device int): when given it is incremented and used for the bias correction instead of
+ * `step`, so the call can be replayed from a CUDA graph. */
 int gnas_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float wd,
-                   float beta1, float beta2, float eps, int step, void* stream);
+                   float beta1, float beta2, float eps, int step, int* step_dev, void* stream);
 
 #ifdef __cplusplus
 }
