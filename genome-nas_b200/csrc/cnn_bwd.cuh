@@ -439,16 +439,21 @@ struct DwBwdJob {
 };
 struct DwBwdBatch { int n, B, C, pad, Wx, Wd; DwBwdJob j[kMaxDw]; };
 
-// CTA: channel c, 8 batch rows (one per warp)
+// CTA: channel c, 8 batch rows (one per warp).  Stride 1 (all but the first conv of strided edges): every lane
+// produces 4 consecutive positions from register windows (128-bit shared loads, static tap indices).
 template <int K, int D, int S>
 __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwBwdBatch P) {
   const DwBwdJob& J = P.j[blockIdx.z];
   const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y * 8 + warp;
   const bool ok = b < P.B;
+  // every depthwise candidate of the reference pads by (K-1)*D/2 (operations_14_9.py:24-28)
+  constexpr int PADC = (K - 1) * D / 2;
+  // du row: index i <-> l = i - OFF, OFF a multiple of 4 >= PADC, so that windows start 16-byte aligned
+  constexpr int OFF = S == 1 ? (PADC + 3) / 4 * 4 : K;
   GNAS_DYN_SMEM(float, smem);
   float* xrow = smem + warp * (P.Wx + P.Wd);   // T(x) with zero halo: index p <-> pos = p - pad
-  float* drow = xrow + P.Wx;                   // du with zero halo: index i <-> l = i - K
+  float* drow = xrow + P.Wx;                   // du with zero halo
   __shared__ float red[8][K + 2];
   float mean = 0.f, rstd = 1.f;
   if (J.tin >= T_BN_RELU) { mean = J.in_stat[c]; rstd = J.in_stat[P.C + c]; }
@@ -460,7 +465,7 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
     }
     const float* dg = J.du + (long long)b * J.dubs + (long long)c * J.Lo;
     for (int i = lane; i < P.Wd; i += 32) {
-      const int l = i - K;
+      const int l = i - OFF;
       drow[i] = (l >= 0 && l < J.Lo) ? dg[l] : 0.f;
     }
   }
@@ -469,30 +474,74 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
 #pragma unroll
   for (int t = 0; t < K; ++t) w[t] = J.wd[c * K + t];
   float s = 0.f, qq = 0.f;
-  if (ok) {
-    float* orow = J.out + (long long)b * J.obs + (long long)c * J.Lin;
-    for (int m = lane; m < J.Lin; m += 32) {
-      float a = 0.f;
-#pragma unroll
-      for (int t = 0; t < K; ++t) {
-        const int num = m + P.pad - t * D;
-        if (S == 1) { a = fmaf(w[t], drow[num + K], a); }
-        else if (num >= 0 && num % S == 0) { a = fmaf(w[t], drow[num / S + K], a); }
-      }
-      const float xv = xg[m];
-      if (J.omode == O_RELU_ACC) { if (xv > 0.f) orow[m] += a; }
-      else { const float v = xv > mean ? a : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv, qq); }
-    }
-  }
-  // depthwise weight gradient: dwd[c,t] += sum_l du[l] * T(x)[l*S + t*D - pad]
   float gw[K];
 #pragma unroll
   for (int t = 0; t < K; ++t) gw[t] = 0.f;
-  if (ok && J.dwd) {
-    for (int l = lane; l < J.Lo; l += 32) {
-      const float dv = drow[l + K];
+  if (ok) {
+    float* orow = J.out + (long long)b * J.obs + (long long)c * J.Lin;
+    if (S == 1) {
+      // dr[m] = sum_t w[t] * du[m + pad - t*D];  window base (drow index) = m0 + pad - (K-1)*D + OFF = m0 + SH
+      constexpr int SH = OFF - PADC;                      // 0..3
+      constexpr int NW = (K - 1) * D + 4 + SH;
+      constexpr int NW4 = (NW + 3) / 4;
+      for (int g4 = lane; g4 * 4 < J.Lin; g4 += 32) {
+        const int m0 = g4 * 4;
+        float dw_[NW4 * 4];
+        const float4* dp = reinterpret_cast<const float4*>(drow + m0);
 #pragma unroll
-      for (int t = 0; t < K; ++t) gw[t] = fmaf(dv, xrow[l * S + t * D], gw[t]);
+        for (int q = 0; q < NW4; ++q) { const float4 v = dp[q]; dw_[4 * q] = v.x; dw_[4 * q + 1] = v.y; dw_[4 * q + 2] = v.z; dw_[4 * q + 3] = v.w; }
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < K; ++t)
+#pragma unroll
+          for (int n = 0; n < 4; ++n) a[n] = fmaf(w[t], dw_[SH + n + (K - 1 - t) * D], a[n]);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int m = m0 + n;
+          if (m < J.Lin) {
+            const float xv = xg[m];
+            if (J.omode == O_RELU_ACC) { if (xv > 0.f) orow[m] += a[n]; }
+            else { const float v = xv > mean ? a[n] : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv, qq); }
+          }
+        }
+      }
+      // dwd[c,t] += sum_l du[l] * T(x)[l + t*D - pad]   (xrow index = l + t*D)
+      if (J.dwd) {
+        constexpr int NR = (K - 1) * D + 4;
+        constexpr int NR4 = (NR + 3) / 4;
+        for (int g4 = lane; g4 * 4 < J.Lo; g4 += 32) {
+          const int l0 = g4 * 4;
+          const float4 dv = *reinterpret_cast<const float4*>(drow + l0 + OFF);
+          const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+          float xw[NR4 * 4];
+          const float4* xp = reinterpret_cast<const float4*>(xrow + l0);
+#pragma unroll
+          for (int q = 0; q < NR4; ++q) { const float4 v = xp[q]; xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w; }
+#pragma unroll
+          for (int t = 0; t < K; ++t)
+#pragma unroll
+            for (int n = 0; n < 4; ++n) gw[t] = fmaf(d4[n], xw[n + t * D], gw[t]);
+        }
+      }
+    } else {
+      for (int m = lane; m < J.Lin; m += 32) {
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+          const int num = m + P.pad - t * D;
+          if (num >= 0 && num % S == 0) a = fmaf(w[t], drow[num / S + OFF], a);
+        }
+        const float xv = xg[m];
+        if (J.omode == O_RELU_ACC) { if (xv > 0.f) orow[m] += a; }
+        else { const float v = xv > mean ? a : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv, qq); }
+      }
+      if (J.dwd) {
+        for (int l = lane; l < J.Lo; l += 32) {
+          const float dv = drow[l + OFF];
+#pragma unroll
+          for (int t = 0; t < K; ++t) gw[t] = fmaf(dv, xrow[l * S + t * D], gw[t]);
+        }
+      }
     }
   }
 #pragma unroll

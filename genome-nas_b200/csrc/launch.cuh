@@ -25,14 +25,16 @@ static inline int choose_tm(int C) {
   if (C % 4 == 0 && C >= 16) return 4;
   return 2;
 }
-static inline int choose_kc(int kw, const int* cins, int n) {
-  int kc = kw == 1 ? 16 : 8;
-  for (;;) {
-    bool ok = true;
-    for (int i = 0; i < n; ++i) ok = ok && (cins[i] % kc == 0);
-    if (ok || kc == 1) return kc;
-    kc >>= 1;
-  }
+static inline int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+// channels of the reduction dimension staged per shared-memory chunk.  Pointwise (KW = 1) weights are small:
+// take as many channels as fit ~96 KB so that a CTA loads once and computes once; KW >= 13 streams 8 at a time.
+static inline int choose_kc(int kw, const int* cins, int n, int cout, int wp) {
+  int g = cins[0];
+  for (int i = 1; i < n; ++i) g = gcd_int(g, cins[i]);
+  if (kw != 1) { int kc = 8; while (g % kc) kc >>= 1; return kc; }
+  int kc = g;
+  while (kc > 8 && kc % 2 == 0 && sizeof(float) * ((size_t)kc * wp + (size_t)kc * cout) > 96 * 1024) kc /= 2;
+  return kc;
 }
 
 // ------------------------------------------------------------------ dense forward
@@ -42,6 +44,9 @@ static void launch_dense_fwd_t(DenseBatch& b, int maxLout, cudaStream_t st) {
   const int nlg = kThreads / ncog;
   b.TL = 4 * nlg;
   const int Wp = ((b.TL - 1) * S + KW + 3) / 4 * 4 + 4;
+  int cins[kMaxDense];
+  for (int i = 0; i < b.n; ++i) cins[i] = b.j[i].Cin;
+  b.KC = choose_kc(KW, cins, b.n, b.Cout, Wp);
   const size_t smem = sizeof(float) * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cout + 2 * b.Cout);
   GNAS_PREP_SMEM((k_dense_fwd<KW, S, TM>), smem);
   dim3 grid(cdiv(maxLout, b.TL), b.B, b.n);
@@ -58,9 +63,8 @@ static void launch_dense_fwd_s(DenseBatch& b, int maxLout, cudaStream_t st) {
 // KW in {1, 13, 15}, S in {1, 2, 3}
 static int launch_dense_fwd(int KW, int S, DenseBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
-  int cins[kMaxDense], maxL = 0;
-  for (int i = 0; i < b.n; ++i) { cins[i] = b.j[i].Cin; maxL = b.j[i].Lout > maxL ? b.j[i].Lout : maxL; }
-  b.KC = choose_kc(KW, cins, b.n);
+  int maxL = 0;
+  for (int i = 0; i < b.n; ++i) maxL = b.j[i].Lout > maxL ? b.j[i].Lout : maxL;
   if (KW == 15 && S == 1) launch_dense_fwd_s<15, 1>(b, maxL, st);
   else if (KW == 15 && S == 2) launch_dense_fwd_s<15, 2>(b, maxL, st);
   else if (KW == 15 && S == 3) launch_dense_fwd_s<15, 3>(b, maxL, st);
@@ -113,6 +117,9 @@ static void launch_dense_dx_t(DxBatch& b, int maxLin, cudaStream_t st) {
   constexpr int NT = (KW + S - 1) / S;
   const int Wu = 4 * b.nq + NT + 1;
   const int Wp = (Wu + 3) / 4 * 4 + 4;
+  int couts[kMaxDense];
+  for (int i = 0; i < b.n; ++i) couts[i] = b.j[i].Cout;
+  b.KC = choose_kc(KW, couts, b.n, b.Cin, Wp);
   const size_t smem = sizeof(float) * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cin + 2 * b.Cin);
   GNAS_PREP_SMEM((k_dense_bwd_dx<KW, S, TM>), smem);
   dim3 grid(cdiv(maxLin, 4 * S * b.nq), b.B, b.n);
@@ -128,9 +135,8 @@ static void launch_dense_dx_s(DxBatch& b, int maxLin, cudaStream_t st) {
 }
 static int launch_dense_dx(int KW, int S, DxBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
-  int couts[kMaxDense], maxL = 0;
-  for (int i = 0; i < b.n; ++i) { couts[i] = b.j[i].Cout; maxL = b.j[i].Lin > maxL ? b.j[i].Lin : maxL; }
-  b.KC = choose_kc(KW, couts, b.n);
+  int maxL = 0;
+  for (int i = 0; i < b.n; ++i) maxL = b.j[i].Lin > maxL ? b.j[i].Lin : maxL;
   if (KW == 15 && S == 1) launch_dense_dx_s<15, 1>(b, maxL, st);
   else if (KW == 15 && S == 2) launch_dense_dx_s<15, 2>(b, maxL, st);
   else if (KW == 15 && S == 3) launch_dense_dx_s<15, 3>(b, maxL, st);
@@ -229,18 +235,27 @@ static int launch_conv_wgrad(int KW, int S, int pad, WgBatch& b, cudaStream_t st
 // ------------------------------------------------------------------ depthwise backward
 template <int K, int D, int S>
 static void launch_dw_bwd_t(DwBwdBatch& b, cudaStream_t st) {
+  constexpr int PADC = (K - 1) * D / 2;
+  constexpr int OFF = S == 1 ? (PADC + 3) / 4 * 4 : K;
   int wx = 0, wd = 0;
   for (int i = 0; i < b.n; ++i) {
-    int a = b.j[i].Lin + 2 * b.pad;
-    const int a2 = (b.j[i].Lo - 1) * S + (K - 1) * D + 1;
+    const int Lin = b.j[i].Lin, Lo = b.j[i].Lo;
+    // x row: index p <-> pos = p - pad; windows of the vector path read up to round4(Lo) + (K-1)*D + 8
+    int a = Lin + 2 * b.pad;
+    const int a2 = (Lo - 1) * S + (K - 1) * D + 1;
+    const int a3 = round_up(Lo, 4) + (K - 1) * D + 8;
     a = a > a2 ? a : a2;
+    a = a > a3 ? a : a3;
     wx = a > wx ? a : wx;
-    const int d = (b.j[i].Lin + b.pad) / S + K + 2;
-    const int d2 = b.j[i].Lo + K + 2;
+    // du row: index i <-> l = i - OFF; vector path reads up to round4(Lin) + (K-1)*D + 12
+    int d = (Lin + b.pad) / S + OFF + 2;
+    const int d2 = Lo + OFF + 8;
+    const int d3 = round_up(Lin, 4) + (K - 1) * D + 12;
+    d = d > d2 ? d : d2;
+    d = d > d3 ? d : d3;
     wd = d > wd ? d : wd;
-    wd = d2 > wd ? d2 : wd;
   }
-  b.Wx = wx + 1; b.Wd = wd;
+  b.Wx = round_up(wx, 4); b.Wd = round_up(wd, 4);
   const size_t smem = sizeof(float) * 8 * (size_t)(b.Wx + b.Wd);
   GNAS_PREP_SMEM((k_dw_bwd<K, D, S>), smem);
   dim3 grid(b.C, cdiv(b.B, 8), b.n);
@@ -248,6 +263,7 @@ static void launch_dw_bwd_t(DwBwdBatch& b, cudaStream_t st) {
 }
 static int launch_dw_bwd(int K, int D, int S, DwBwdBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
+  if (b.pad != (K - 1) * D / 2) { set_error("dw_bwd: padding must be (K-1)*D/2"); return GNAS_ERR_UNSUPPORTED; }
 #define GNAS_DW_CASE(k, d, s) if (K == k && D == d && S == s) launch_dw_bwd_t<k, d, s>(b, st); else
   GNAS_DW_CASE(15, 1, 1) GNAS_DW_CASE(15, 1, 2) GNAS_DW_CASE(15, 1, 3)
   GNAS_DW_CASE(9, 1, 1) GNAS_DW_CASE(9, 1, 2) GNAS_DW_CASE(9, 1, 3)

@@ -431,16 +431,17 @@ static __global__ void __launch_bounds__(256) k_rhn_bwd_tinit(float* dsT, const 
   }
 }
 
-// node = i+1: dr = BN_bwd(ds_{i+1}); per edge (i,j): dc, dh (in place over c, h), direct ds_j term, dprobs
+// node = i+1: dr = BN_bwd(ds_{i+1}); edge (i, j = blockIdx.y): dc, dh (in place over c, h), direct ds_j term,
+// dprobs.  One warp per hidden column; the BN reduction is recomputed per edge (two loads per row).
 static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem(const __grid_constant__ RhnBwd P) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * 8 + warp;
-  const int i = P.node - 1;
+  const int i = P.node - 1, j = blockIdx.y;
   const int B = P.B, BP = P.BP, H = P.H;
   const long long HB = (long long)H * BP;
-  __shared__ float red[8][8][4];
-  for (int q = threadIdx.x; q < 8 * 8 * 4; q += kThreads) (&red[0][0][0])[q] = 0.f;
-  __syncthreads();
+  const int p = i * (i + 1) / 2 + j;
+  __shared__ float red[8][4];
+  float dpl[4] = {0.f, 0.f, 0.f, 0.f};
   if (n < H) {
     const size_t row = (size_t)n * BP;
     const float* dsr = P.dsT + (size_t)P.node * HB + row;
@@ -452,18 +453,17 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem(const __grid_c
     const float S1 = warp_sum(d0 + d1) / (float)B;
     const float S2 = warp_sum(d0 * h0 + d1 * h1) / (float)B;
     const float dr0 = rstd * (d0 - S1 - h0 * S2), dr1 = rstd * (d1 - S1 - h1 * S2);
-    for (int j = 0; j <= i; ++j) {
-      const int p = i * (i + 1) / 2 + j;
-      float pk[4], dpl[4] = {0.f, 0.f, 0.f, 0.f}, q = 0.f;
+    float pk[4], q = 0.f;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int ix = P.tb.pidx[p][k]; pk[k] = ix >= 0 ? P.probs[ix] : 0.f; q += pk[k]; }
-      float* cp = P.CHT + (((size_t)P.t * 36 + p) * 2) * HB + row;
-      float* hp = cp + HB;
-      const float* sjr = P.ST + ((size_t)P.t * 9 + j) * HB + row;
-      float* dsj = P.dsT + (size_t)j * HB + row;
-      for (int half = 0; half < 2; ++half) {
-        const int m = lane + 32 * half;
-        if (m >= BP) continue;
+    for (int k = 0; k < 4; ++k) { const int ix = P.tb.pidx[p][k]; pk[k] = ix >= 0 ? P.probs[ix] : 0.f; q += pk[k]; }
+    float* cp = P.CHT + (((size_t)P.t * 36 + p) * 2) * HB + row;
+    float* hp = cp + HB;
+    const float* sjr = P.ST + ((size_t)P.t * 9 + j) * HB + row;
+    float* dsj = P.dsT + (size_t)j * HB + row;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int m = lane + 32 * half;
+      if (m < BP) {
         float dc = 0.f, dh = 0.f;
         if (m < B) {
           const float dr = half ? dr1 : dr0;
@@ -472,7 +472,7 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem(const __grid_c
           float F = 0.f, Fp = 0.f;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if (P.tb.pidx[p][k] >= 0) {
+            if (pk[k] != 0.f || P.tb.pidx[p][k] >= 0) {
               const float f = act_f(k, h);
               F = fmaf(pk[k], f, F); Fp = fmaf(pk[k], act_df(k, h), Fp);
               dpl[k] = fmaf(dr, sj + g * (f - sj), dpl[k]);
@@ -484,18 +484,17 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem(const __grid_c
         }
         cp[m] = dc; hp[m] = dh;
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { const float v = warp_sum(dpl[k]); if (lane == 0) red[warp][j][k] = v; }
     }
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const float v = warp_sum(dpl[k]); if (lane == 0) red[warp][k] = v; }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int j = threadIdx.x >> 2, k = threadIdx.x & 3;
-    if (j <= i) {
+  if (threadIdx.x < 4) {
+    const int k = threadIdx.x;
+    if (P.tb.pidx[p][k] >= 0) {
       float v = 0.f;
-      for (int w = 0; w < 8; ++w) v += red[w][j][k];
-      const int p = i * (i + 1) / 2 + j;
-      if (P.tb.pidx[p][k] >= 0) atomicAdd(&P.dpacc[p * 4 + k], (double)v);
+      for (int w = 0; w < 8; ++w) v += red[w][k];
+      atomicAdd(&P.dpacc[p * 4 + k], (double)v);
     }
   }
 }
@@ -538,49 +537,68 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem0(const __grid_
 }
 
 // out_z[n][m] += mask[n][m] * sum_k W[n][k] * D_z[k][m]   (split-K, atomics)
+// CTA tile: 64 rows n x BP columns m, K range = K / ksplit, cp.async double-buffered 32-row K chunks.
 struct RhnGemm {
   int Nrows, K, BP, nz, ksplit, Hsplit;   // rows >= Hsplit go to out2/mask2 (stage 0: dx rows | dh rows)
   const float* W; int ldw;
   const float* D[8]; float* out[8];
   const float* mask; float* out2; const float* mask2;
 };
+constexpr int kGemmKC = 32, kGemmWP = kGemmKC + 4;
 static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_gemm(const __grid_constant__ RhnGemm P) {
   const int z = blockIdx.z;
-  const int n0 = blockIdx.x * 32;
+  const int n0 = blockIdx.x * 64;
   const int kper = P.K / P.ksplit;
   const int kbeg = blockIdx.y * kper;
   const int BP = P.BP;
   const int tid = threadIdx.x;
   const int ncg = BP / 4;
-  const int rp = tid / ncg, cg = tid - rp * ncg;
-  const bool active = rp < 16;
-  __shared__ float Wt[32][34];
-  GNAS_DYN_SMEM(float, Ds);    // [32][BP]
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const int rq = tid / ncg, cg = tid - rq * ncg;
+  const bool active = rq < 16;
+  __shared__ __align__(16) float Wsm[2][64 * kGemmWP];
+  __shared__ __align__(16) float Dsm[2][kGemmKC * kMaxBP];
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   const float* Dz = P.D[z];
-  for (int k0 = kbeg; k0 < kbeg + kper; k0 += 32) {
-    for (int i = tid; i < 32 * 32; i += kThreads) {
-      const int r = i >> 5, k = i & 31;
-      Wt[k][r] = (n0 + r < P.Nrows) ? P.W[(size_t)(n0 + r) * P.ldw + k0 + k] : 0.f;
+  const int nch = kper / kGemmKC;
+  auto issue = [&](int c) {
+    const int k0 = kbeg + c * kGemmKC;
+    float* wd = Wsm[c & 1];
+    float* dd = Dsm[c & 1];
+    for (int i = tid; i < 64 * (kGemmKC / 4); i += kThreads) {       // W rows: 8 x 16-byte pieces each
+      const int r = i / (kGemmKC / 4), q = i - r * (kGemmKC / 4);
+      const int n = n0 + r < P.Nrows ? n0 + r : P.Nrows - 1;
+      cp_async16(wd + r * kGemmWP + 4 * q, P.W + (size_t)n * P.ldw + k0 + 4 * q);
     }
-    for (int i = tid; i < 32 * BP / 4; i += kThreads)
-      reinterpret_cast<float4*>(Ds)[i] = reinterpret_cast<const float4*>(Dz + (size_t)k0 * BP)[i];
+    for (int i = tid; i < kGemmKC * BP / 4; i += kThreads) cp_async16(dd + 4 * i, Dz + (size_t)k0 * BP + 4 * i);
+    cp_async_commit();
+  };
+  issue(0);
+  for (int c = 0; c < nch; ++c) {
+    if (c + 1 < nch) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
     if (active) {
+      const float* wr = Wsm[c & 1] + (4 * rq) * kGemmWP;
+      const float* dr = Dsm[c & 1] + 4 * cg;
 #pragma unroll 8
-      for (int k = 0; k < 32; ++k) {
-        const float w0 = Wt[k][2 * rp], w1 = Wt[k][2 * rp + 1];
-        const float4 d = *reinterpret_cast<const float4*>(Ds + k * BP + 4 * cg);
+      for (int k = 0; k < kGemmKC; ++k) {
+        const float w0 = wr[k], w1 = wr[kGemmWP + k], w2 = wr[2 * kGemmWP + k], w3 = wr[3 * kGemmWP + k];
+        const float4 d = *reinterpret_cast<const float4*>(dr + k * BP);
         acc[0][0] = fmaf(w0, d.x, acc[0][0]); acc[0][1] = fmaf(w0, d.y, acc[0][1]); acc[0][2] = fmaf(w0, d.z, acc[0][2]); acc[0][3] = fmaf(w0, d.w, acc[0][3]);
         acc[1][0] = fmaf(w1, d.x, acc[1][0]); acc[1][1] = fmaf(w1, d.y, acc[1][1]); acc[1][2] = fmaf(w1, d.z, acc[1][2]); acc[1][3] = fmaf(w1, d.w, acc[1][3]);
+        acc[2][0] = fmaf(w2, d.x, acc[2][0]); acc[2][1] = fmaf(w2, d.y, acc[2][1]); acc[2][2] = fmaf(w2, d.z, acc[2][2]); acc[2][3] = fmaf(w2, d.w, acc[2][3]);
+        acc[3][0] = fmaf(w3, d.x, acc[3][0]); acc[3][1] = fmaf(w3, d.y, acc[3][1]); acc[3][2] = fmaf(w3, d.z, acc[3][2]); acc[3][3] = fmaf(w3, d.w, acc[3][3]);
       }
     }
     __syncthreads();
   }
   if (active) {
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int n = n0 + 2 * rp + a;
+    for (int a = 0; a < 4; ++a) {
+      const int n = n0 + 4 * rq + a;
       if (n >= P.Nrows) continue;
       float* o; const float* mk;
       if (n < P.Hsplit) { o = P.out[z] + (size_t)n * BP; mk = P.mask + (size_t)n * BP; }
@@ -776,7 +794,8 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
   bp.probs = probs; bp.dout = dout; bp.dsT = scratch + p.dsT; bp.dpacc = reinterpret_cast<double*>(scratch + p.dpacc);
   bp.tb = tb;
   const int eb = (H + 7) / 8;
-  const size_t gsm = sizeof(float) * 32 * BP;
+  int ksplit = 1;                       // split K = 2H so that each CTA still sees >= 2 chunks of 32
+  while (ksplit < 8 && (2 * H) % (ksplit * 2 * kGemmKC) == 0 && (2 * H) / (ksplit * 2) >= 2 * kGemmKC) ksplit *= 2;
   for (int t = T - 1; t >= 0; --t) {
     float* dh_cur = dhbuf[(T - 1 - t) & 1];
     float* dh_next = dhbuf[(T - t) & 1];
@@ -784,25 +803,25 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
     GNAS_LAUNCH(k_rhn_bwd_tinit, dim3(ewb(9 * HB)), dim3(256), 0, st, scratch + p.dsT, (const float*)dh_cur, HB);
     for (int i = 7; i >= 0; --i) {
       bp.node = i + 1;
-      GNAS_LAUNCH(k_rhn_bwd_elem, dim3(eb), dim3(kThreads), 0, st, bp);
+      GNAS_LAUNCH(k_rhn_bwd_elem, dim3(eb, i + 1), dim3(kThreads), 0, st, bp);
       RhnGemm g;
-      g.Nrows = H; g.K = 2 * H; g.BP = BP; g.nz = i + 1; g.ksplit = (2 * H) / 32 >= 8 ? 8 : 1; g.Hsplit = H;
+      g.Nrows = H; g.K = 2 * H; g.BP = BP; g.nz = i + 1; g.ksplit = ksplit; g.Hsplit = H;
       g.W = Ws + (size_t)i * H * 2 * H; g.ldw = 2 * H;
       for (int j = 0; j <= i; ++j) {
         g.D[j] = ws + p.CHT + (((size_t)t * 36 + i * (i + 1) / 2 + j) * 2) * HB;
         g.out[j] = scratch + p.dsT + (size_t)j * HB;
       }
       g.mask = ws + p.hmT; g.out2 = nullptr; g.mask2 = nullptr;
-      GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((H + 31) / 32, g.ksplit, i + 1), dim3(kThreads), gsm, st, g);
+      GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((H + 63) / 64, g.ksplit, i + 1), dim3(kThreads), 0, st, g);
     }
     GNAS_LAUNCH(k_rhn_bwd_elem0, dim3(eb), dim3(kThreads), 0, st, bp);
     RhnGemm g;
-    g.Nrows = 2 * H; g.K = 2 * H; g.BP = BP; g.nz = 1; g.ksplit = (2 * H) / 32 >= 8 ? 8 : 1; g.Hsplit = H;
+    g.Nrows = 2 * H; g.K = 2 * H; g.BP = BP; g.nz = 1; g.ksplit = ksplit; g.Hsplit = H;
     g.W = W0; g.ldw = 2 * H;
     g.D[0] = ws + p.C0T + ((size_t)t * 2) * HB;
     g.out[0] = scratch + p.dxT + (size_t)t * HB; g.mask = ws + p.xkT;
     g.out2 = dh_next; g.mask2 = ws + p.hmT;
-    GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((2 * H + 31) / 32, g.ksplit, 1), dim3(kThreads), gsm, st, g);
+    GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((2 * H + 63) / 64, g.ksplit, 1), dim3(kThreads), 0, st, g);
   }
   // outputs: dx [T][B][H], dh0 [B][H], dprobs
   GNAS_LAUNCH(k_rhn_untranspose, dim3(ewb((long long)T * B * H)), dim3(256), 0, st, (const float*)(scratch + p.dxT), dx, T, B, BP, H);

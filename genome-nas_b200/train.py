@@ -60,8 +60,8 @@ class SearchStep:
             raise RuntimeError("model parameters were re-allocated: build a new SearchStep")
         return r.flat, r.ensure_grads()
 
-    def alpha_step(self, x_valid, y_valid):
-        lib, h = _lib.lib(), self.h
+    def alpha_backward(self, x_valid, y_valid):
+        """fwd + bwd of the validation BCE with the weight-gradient kernels switched off (architect.py:69-72)."""
         flat, g = self._refresh()
         model = self.model
         g[:self.n_alpha].zero_()
@@ -72,15 +72,29 @@ class SearchStep:
             loss.backward()
         finally:
             model.set_weight_grads(True)
-        ga = g[:self.n_alpha]
+        return loss.detach()
+
+    def reduce_alpha_gradients(self):
+        flat, g = self._refresh()
         if self.world > 1:
+            ga = g[:self.n_alpha]
             torch.distributed.all_reduce(ga, group=self.pg)
             ga.div_(self.world)
-        _lib.check(lib.gnas_adam_step(_lib.ptr(flat), _lib.ptr(ga), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v),
+
+    def alpha_update(self):
+        """Adam on the three alpha tensors (architect.py:42,66)."""
+        lib, h = _lib.lib(), self.h
+        flat, g = self._refresh()
+        _lib.check(lib.gnas_adam_step(_lib.ptr(flat), _lib.ptr(g), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v),
                                       self.n_alpha, h.arch_lr, h.arch_wd, h.adam_betas[0], h.adam_betas[1], h.adam_eps,
                                       0, _lib.ptr(self.t_adam), _lib.stream_ptr(flat)), "adam_step")
         _lib.LAUNCHES += 1
-        return loss.detach()
+
+    def alpha_step(self, x_valid, y_valid):
+        loss = self.alpha_backward(x_valid, y_valid)
+        self.reduce_alpha_gradients()
+        self.alpha_update()
+        return loss
 
     def weight_backward(self, x_train, y_train, zero=True):
         """fwd + bwd of BCE + beta*TAR on a training batch; gradients land in the flat buffer."""
@@ -140,7 +154,15 @@ class SearchStep:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self._draw_static_masks()
-        self.graph.replay()
+        if self.world == 1:
+            self.graph.replay()
+        else:                       # NCCL allreduces stay outside the graphs
+            g1, g2, g3 = self.graph
+            g1.replay()
+            self.reduce_alpha_gradients()
+            g2.replay()
+            self.reduce_gradients()
+            g3.replay()
         return self._static_out
 
     # ---- CUDA-graph mode: the ~3.7 k launches of a step are replayed from one captured graph --------------
@@ -179,11 +201,25 @@ class SearchStep:
                     self._step_eager(*self._static_in)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
-            graph = torch.cuda.CUDAGraph()
             cursor[0] = 0
             n0 = _lib.kernel_launches()
-            with torch.cuda.graph(graph):
-                self._static_out = self._step_eager(*self._static_in)
+            xt, yt, xv, yv = self._static_in
+            if self.world == 1:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._static_out = self._step_eager(xt, yt, xv, yv)
+            else:
+                pool = torch.cuda.graph_pool_handle()
+                g1, g2, g3 = (torch.cuda.CUDAGraph() for _ in range(3))
+                with torch.cuda.graph(g1, pool=pool):
+                    la = self.alpha_backward(xv, yv)
+                with torch.cuda.graph(g2, pool=pool):
+                    self.alpha_update()
+                    lw, raw, logits = self.weight_backward(xt, yt)
+                with torch.cuda.graph(g3, pool=pool):
+                    self.apply_weight_update()
+                self._static_out = (la, lw, raw, logits)
+                graph = (g1, g2, g3)
             self.graph_launches = _lib.kernel_launches() - n0      # our kernels inside one replay
             self.graph = graph
         except Exception:

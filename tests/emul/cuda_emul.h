@@ -32,7 +32,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __launch_bounds__(...)
 #define __grid_constant__
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static thread_local
 #define __restrict__ __restrict
 
