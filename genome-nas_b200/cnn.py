@@ -67,7 +67,7 @@ class _FusedCellFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, s0, s1, weights, _anchor):
         lib = _lib.lib()
-        region = region_of(runner)
+        region = region_of(runner, device=s1.device)
         has_pre = runner._has_pre
         s1 = _lib.require(s1.contiguous(), "s1")
         if has_pre:
@@ -100,7 +100,7 @@ class _FusedCellFunction(torch.autograd.Function):
         s0, s1, weights, out, ws = ctx.saved_tensors
         has_pre = runner._has_pre
         dout = _lib.require(dout.contiguous(), "grad_output")
-        region = region_of(runner)
+        region = region_of(runner, device=s1.device)
         gflat = region.ensure_grads() if ctx.need_wgrad else None
         dev = s1.device
         scratch = torch.empty(ctx.bwd_floats, dtype=torch.float32, device=dev)

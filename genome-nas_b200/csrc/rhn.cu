@@ -162,11 +162,14 @@ struct RhnFwd {
   RhnTable tb;
 };
 
-__device__ __forceinline__ bool grid_barrier(unsigned* bar, int* abort_flag, unsigned target, int* s_abort) {
-  __syncthreads();
+// Grid barrier split into arrive / wait so that work that does not gate the next stage (stashing the
+// pre-activations for backward, the contributions to later nodes) overlaps the wait.
+__device__ __forceinline__ void grid_arrive(unsigned* bar) {
+  __syncthreads();                       // every thread's ring writes are issued
+  if (threadIdx.x == 0) { __threadfence(); atomicAdd(bar, 1u); }
+}
+__device__ __forceinline__ bool grid_wait(unsigned* bar, int* abort_flag, unsigned target, int* s_abort) {
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
     const long long t0 = gnas_clock();
     int ab = 0;
     while (ld_acquire_u32(bar) < target) {
@@ -189,10 +192,14 @@ __device__ __forceinline__ int rhn_ks(int BP, int N) {
   return a >= 8 ? 8 : (a >= 4 ? 4 : (a >= 2 ? 2 : 1));
 }
 
-// C[m][n] partial = sum_k A[k][m] * W[k][n]; A streamed from global ([K][BP], already masked) in kKCH-row chunks
-// with cp.async double buffering; W slices resident in shared memory.  Result (K-split partials) -> part.
+constexpr int kStages = 4;    // cp.async ring depth of the streamed operand
+
+// C[m][n] partial = sum_k A[k][m] * W[k][n]; A ([K][BP], already masked) is streamed from global/L2 through a
+// kStages-deep cp.async ring of kKCH-row chunks (one __syncthreads per chunk); the W slices are resident in
+// shared memory.  The K-split partials are left in `part`, which ALIASES the ring (safe: written after the
+// last chunk has been consumed by every thread).
 __device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const float* __restrict__ A1, int K0, int K,
-                                         int BP, int N, const float* wbase, int wstride_i, int H_w, bool stage0,
+                                         int BP, int N, const float* wbase, int wstride_i, bool stage0,
                                          float* abuf, float* part) {
   const int tid = threadIdx.x;
   const int nrg = BP / 4, ncg = N / 4;
@@ -206,22 +213,25 @@ __device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const flo
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   // W column group: stage 0 -> W0s[k][8]; stage j -> Wss[i][k][8] with i = cg / 2
   const float* wcol = stage0 ? wbase + cg * 4 : wbase + (size_t)(cg >> 1) * wstride_i + (cg & 1) * 4;
-  (void)H_w;
   const int nch = K / kKCH;
   const int f4_per_chunk = kKCH * BP / 4;
   auto issue = [&](int c) {
-    float* dst = abuf + (c & 1) * kKCH * BP;
-    const int k0 = c * kKCH;
-    const float* src = (k0 < K0) ? A0 + (size_t)k0 * BP : A1 + (size_t)(k0 - K0) * BP;
-    for (int i = tid; i < f4_per_chunk; i += kThreads) cp_async16(dst + 4 * i, src + 4 * i);
-    cp_async_commit();
+    if (c < nch) {
+      float* dst = abuf + (c % kStages) * kKCH * BP;
+      const int k0 = c * kKCH;
+      const float* src = (k0 < K0) ? A0 + (size_t)k0 * BP : A1 + (size_t)(k0 - K0) * BP;
+      for (int i = tid; i < f4_per_chunk; i += kThreads) cp_async16(dst + 4 * i, src + 4 * i);
+    }
+    cp_async_commit();                   // always commit (possibly empty) so that group counting stays uniform
   };
-  issue(0);
+#pragma unroll
+  for (int c = 0; c < kStages - 1; ++c) issue(c);
   for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();
+    cp_async_wait<kStages - 2>();        // chunk c has landed (for this thread's copies)
+    __syncthreads();                     // ... for everyone's; and everyone is done with chunk c-1
+    issue(c + kStages - 1);              // refill the slot chunk c-1 occupied
     if (active) {
-      const float* as = abuf + (c & 1) * kKCH * BP + rg * 4;
+      const float* as = abuf + (c % kStages) * kKCH * BP + rg * 4;
       const float* wk = wcol + (size_t)(c * kKCH) * 8;
 #pragma unroll 4
       for (int k = ks; k < kKCH; k += KS) {
@@ -233,8 +243,9 @@ __device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const flo
         acc[3][0] = fmaf(a.w, w.x, acc[3][0]); acc[3][1] = fmaf(a.w, w.y, acc[3][1]); acc[3][2] = fmaf(a.w, w.z, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
       }
     }
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();                       // ring no longer read: `part` may overwrite it
   if (active) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -251,13 +262,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
   GNAS_DYN_SMEM(float, smem);
   float* W0s = smem;                          // [2H][8]
   float* Wss = W0s + (size_t)2 * H * 8;       // [8][H][8]
-  float* abuf = Wss + (size_t)8 * H * 8;      // [2][kKCH][BP]
-  float* part = abuf + 2 * kKCH * BP;         // [KS][BP][N]  (<= BP*64 floats)
-  float* accn = part + BP * 64;               // [8][BP][4]  pending node accumulators
+  float* abuf = Wss + (size_t)8 * H * 8;      // [kStages][kKCH][BP]  streamed operand ring
+  float* part = abuf;                         // [KS][BP][N] (<= BP*64 floats) aliases the ring
+  float* accn = abuf + kStages * kKCH * BP;   // [8][BP][4]  pending node accumulators
   float* sloc = accn + 8 * BP * 4;            // [9][BP][4]  own columns of s_0..s_8
   float* hloc = sloc + 9 * BP * 4;            // [BP][4]     own columns of h_{t-1}
   float* hml = hloc + BP * 4;                 // [BP][4]     own columns of the hidden mask
-  float* pp = hml + BP * 4;                   // [36][4] probabilities, [36] q
+  float* tmp0 = hml + BP * 4;                 // [BP][4]     raw s_0 before BN
+  float* pp = tmp0 + BP * 4;                  // [36][4] probabilities, [36] q
   float* pq = pp + 36 * 4;
   float* run = pq + 36;                       // [2][4] running mean | var of own columns
   __shared__ int s_abort;
@@ -291,7 +303,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
   unsigned bar_target = 0;
   const float invB = 1.f / (float)B;
 
-  // BatchNorm over the batch for the 4 own columns of `src` ([BP][4]); warp w < 4 handles column w.
+  // BatchNorm over the batch for the 4 own columns of `src` ([BP][4]); warp w < 4 handles column w and
+  // publishes the masked state to the ring (what the other CTAs wait for).
   auto bn_publish = [&](const float* src, int t, int stage) {
     if (warp < kNC) {
       const int col = warp;
@@ -316,23 +329,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
         float* st = P.stat + ((size_t)t * 9 + stage) * 2 * H;
         st[n] = mean; st[H + n] = rstd;
       }
-      float* STr = P.ST + ((size_t)t * 9 + stage) * HB + (size_t)n * BP;
       float* rgr = P.ring + (size_t)stage * HB + (size_t)n * BP;
       for (int m = lane; m < BP; m += 32) {
         const float v = m < B ? ((m < 32 ? v0 : v1) - mean) * rstd : 0.f;
         sloc[(stage * BP + m) * 4 + col] = v;
-        STr[m] = v;
         rgr[m] = v * hml[m * 4 + col];
       }
+    }
+  };
+  // unmasked state for backward (off the critical path)
+  auto stash_state = [&](int t, int stage) {
+    for (int i = tid; i < BP * 4; i += kThreads) {
+      const int col = i / BP, m = i - col * BP;
+      P.ST[((size_t)t * 9 + stage) * HB + (size_t)(n0 + col) * BP + m] = sloc[(stage * BP + m) * 4 + col];
+    }
+  };
+  // contribution of edge (i, j) to node i from c|h in `part`
+  auto edge_item = [&](int t, int j, int irel, int m, int col, int N, int KS, bool store) {
+    const int i = j + irel;
+    const int p = i * (i + 1) / 2 + j;
+    float c = 0.f, h = 0.f;
+    for (int s = 0; s < KS; ++s) {
+      c += part[(size_t)(s * BP + m) * N + irel * 8 + col];
+      h += part[(size_t)(s * BP + m) * N + irel * 8 + 4 + col];
+    }
+    if (store) {
+      float* chp = P.CHT + (((size_t)t * 36 + p) * 2) * HB + (size_t)(n0 + col) * BP + m;
+      chp[0] = c; chp[HB] = h;
+    }
+    const float q = pq[p];
+    const float p0 = pp[p * 4], p1 = pp[p * 4 + 1], p2 = pp[p * 4 + 2], p3 = pp[p * 4 + 3];
+    if (p0 != 0.f || p1 != 0.f || p2 != 0.f || p3 != 0.f) {
+      const float sj = sloc[(j * BP + m) * 4 + col];
+      const float g = sigmoidf_(c);
+      float F = 0.f;
+      if (p0 != 0.f) F = fmaf(p0, tanhf(h), F);
+      if (p1 != 0.f) F = fmaf(p1, h, F);
+      if (p2 != 0.f) F = fmaf(p2, sigmoidf_(h), F);
+      if (p3 != 0.f) F = fmaf(p3, h > 0.f ? h : 0.f, F);
+      accn[(i * BP + m) * 4 + col] += q * sj + g * (F - q * sj);
     }
   };
 
   for (int t = 0; t < T; ++t) {
     // ---------------- stage 0: [c0|h0] = [x_t*xm | h*hm] W0 ; s_0 = BN(h + sig(c0)(tanh(h0) - h))
-    rhn_gemm(P.xmT + (size_t)t * HB, P.ring + 9 * HB, H, 2 * H, BP, 8, W0s, 0, H, true, abuf, part);
+    rhn_gemm(P.xmT + (size_t)t * HB, P.ring + 9 * HB, H, 2 * H, BP, 8, W0s, 0, true, abuf, part);
     {
       const int KS = rhn_ks(BP, 8);
-      float* tmp = accn;   // borrow node-0..: use part tail instead? accn[0] is empty at this point of the step
       for (int i = tid; i < B * 4; i += kThreads) {
         const int col = i / B, m = i - col * B;
         float c = 0.f, h = 0.f;
@@ -340,50 +383,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
         P.C0T[((size_t)t * 2 + 0) * HB + (size_t)(n0 + col) * BP + m] = c;
         P.C0T[((size_t)t * 2 + 1) * HB + (size_t)(n0 + col) * BP + m] = h;
         const float hp = hloc[m * 4 + col];
-        tmp[(7 * BP + m) * 4 + col] = hp + sigmoidf_(c) * (tanhf(h) - hp);   // node-7 slot is untouched until stage 0 GEMM of s_0 is consumed
+        tmp0[m * 4 + col] = hp + sigmoidf_(c) * (tanhf(h) - hp);
       }
       __syncthreads();
-      bn_publish(accn + 7 * BP * 4, t, 0);
-      __syncthreads();
-      for (int i = tid; i < BP * 4; i += kThreads) accn[7 * BP * 4 + i] = 0.f;
+      bn_publish(tmp0, t, 0);
     }
+    grid_arrive(P.bar);
+    stash_state(t, 0);
     bar_target += gridDim.x;
-    if (grid_barrier(P.bar, P.abort_flag, bar_target, &s_abort)) return;
-    // ---------------- stages j = 0..7: multiply s_j with the slices of Ws[j..7], finish node j -> s_{j+1}
+    if (grid_wait(P.bar, P.abort_flag, bar_target, &s_abort)) return;
+    // ---------------- stages j = 0..7: multiply s_j with the slices of Ws[j..7]; node j -> s_{j+1} first
     for (int j = 0; j < 8; ++j) {
       const int N = 8 * (8 - j);
-      rhn_gemm(P.ring + (size_t)j * HB, nullptr, H, H, BP, N, Wss + (size_t)j * H * 8, H * 8, H, false, abuf, part);
+      rhn_gemm(P.ring + (size_t)j * HB, nullptr, H, H, BP, N, Wss + (size_t)j * H * 8, H * 8, false, abuf, part);
       const int KS = rhn_ks(BP, N);
-      const int items = (8 - j) * 4 * B;
-      for (int it = tid; it < items; it += kThreads) {
-        const int m = it % B;
-        const int col = (it / B) & 3;
-        const int irel = it / (4 * B);
-        const int i = j + irel;
-        const int p = i * (i + 1) / 2 + j;
-        float c = 0.f, h = 0.f;
-        for (int s = 0; s < KS; ++s) {
-          c += part[(size_t)(s * BP + m) * N + irel * 8 + col];
-          h += part[(size_t)(s * BP + m) * N + irel * 8 + 4 + col];
-        }
-        float* chp = P.CHT + (((size_t)t * 36 + p) * 2) * HB + (size_t)(n0 + col) * BP + m;
-        chp[0] = c; chp[HB] = h;
-        const float q = pq[p];
-        if (q != 0.f || pp[p * 4] != 0.f || pp[p * 4 + 1] != 0.f || pp[p * 4 + 2] != 0.f || pp[p * 4 + 3] != 0.f) {
-          const float sj = sloc[(j * BP + m) * 4 + col];
-          const float g = sigmoidf_(c);
-          float F = 0.f;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) { const float pk = pp[p * 4 + k]; if (pk != 0.f) F = fmaf(pk, act_f(k, h), F); }
-          accn[(i * BP + m) * 4 + col] += q * sj + g * (F - q * sj);
-        }
-      }
+      // critical: edge (j, j) completes node j
+      for (int it = tid; it < 4 * B; it += kThreads) edge_item(t, j, 0, it % B, it / B, N, KS, false);
       __syncthreads();
       bn_publish(accn + j * BP * 4, t, j + 1);
-      __syncthreads();
-      for (int i = tid; i < BP * 4; i += kThreads) accn[j * BP * 4 + i] = 0.f;
-      if (j == 7) {
-        // h_t = mean(s_1..s_8)  (model_search.py:96)
+      const bool last = j == 7;
+      if (last) {
+        __syncthreads();
+        // h_t = mean(s_1..s_8)  (model_search.py:96); its masked copy feeds stage 0 of the next step
         for (int i = tid; i < BP * 4; i += kThreads) {
           const int m = i >> 2, col = i & 3;
           float a = 0.f;
@@ -392,16 +413,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
           a *= 0.125f;
           if (m >= B) a = 0.f;
           hloc[i] = a;
-          P.HT[(size_t)t * HB + (size_t)(n0 + col) * BP + m] = a;
           P.ring[9 * HB + (size_t)(n0 + col) * BP + m] = a * hml[i];
         }
-        __syncthreads();
+      }
+      const bool need_barrier = !last || t + 1 < T;
+      if (need_barrier) grid_arrive(P.bar); else __syncthreads();
+      // off the critical path: stash for backward, contributions of s_j to the later nodes, bookkeeping
+      for (int it = tid; it < 4 * B; it += kThreads) {        // pre-activations of edge (j, j)
+        const int m = it % B, col = it / B;
+        float c = 0.f, h = 0.f;
+        for (int s = 0; s < KS; ++s) { c += part[(size_t)(s * BP + m) * N + col]; h += part[(size_t)(s * BP + m) * N + 4 + col]; }
+        float* chp = P.CHT + (((size_t)t * 36 + j * (j + 1) / 2 + j) * 2) * HB + (size_t)(n0 + col) * BP + m;
+        chp[0] = c; chp[HB] = h;
+      }
+      for (int it = tid; it < (7 - j) * 4 * B; it += kThreads) {
+        const int m = it % B, col = (it / B) & 3, irel = 1 + it / (4 * B);
+        edge_item(t, j, irel, m, col, N, KS, true);
+      }
+      stash_state(t, j + 1);
+      for (int i = tid; i < BP * 4; i += kThreads) accn[j * BP * 4 + i] = 0.f;
+      if (last) {
+        for (int i = tid; i < BP * 4; i += kThreads) {
+          const int col = i / BP, m = i - col * BP;
+          P.HT[(size_t)t * HB + (size_t)(n0 + col) * BP + m] = hloc[m * 4 + col];
+        }
         for (int m = tid; m < B; m += kThreads)
           *reinterpret_cast<float4*>(P.out + ((size_t)t * B + m) * H + n0) =
               make_float4(hloc[m * 4], hloc[m * 4 + 1], hloc[m * 4 + 2], hloc[m * 4 + 3]);
       }
       bar_target += gridDim.x;
-      if (j < 7 || t + 1 < T) { if (grid_barrier(P.bar, P.abort_flag, bar_target, &s_abort)) return; }
+      if (need_barrier) { if (grid_wait(P.bar, P.abort_flag, bar_target, &s_abort)) return; }
+      else __syncthreads();
     }
   }
   if (P.training && P.running && tid < 8) P.running[(tid >> 2) * H + n0 + (tid & 3)] = run[tid];
@@ -740,8 +782,8 @@ extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const floa
   f.out = out; f.running = bn_running;
   f.bar = reinterpret_cast<unsigned*>(ws + p.bar); f.abort_flag = reinterpret_cast<int*>(ws + p.bar) + 8;
   rhn_table(d, f.tb);
-  const size_t smem = sizeof(float) * ((size_t)2 * H * 8 + (size_t)8 * H * 8 + 2 * kKCH * BP + (size_t)BP * 64 +
-                                       8 * BP * 4 + 9 * BP * 4 + 2 * BP * 4 + 36 * 5 + 8 + 8);
+  const size_t smem = sizeof(float) * ((size_t)2 * H * 8 + (size_t)8 * H * 8 + (size_t)kStages * kKCH * BP +
+                                       8 * BP * 4 + 9 * BP * 4 + 3 * BP * 4 + 36 * 5 + 8 + 8);
   const int grid = H / kNC;
 #ifdef GNAS_EMUL
   GNAS_LAUNCH_COOP(k_rhn_forward, dim3(grid), dim3(kThreads), smem, st, f);

@@ -73,13 +73,17 @@ class FlatRegion:
             probe += (bufs[0][1].data_ptr(), bufs[-1][1].data_ptr(), bufs[0][1].device)
         return probe
 
-    def ensure(self):
+    def ensure(self, device=None):
         named = [(n, p) for n, p in self.module.named_parameters() if n not in self.exclude]
         self._names = [n for n, _ in named]
         self._params = [p for _, p in named]
         bufs = self._bufs()
-        if not named and not bufs:
-            raise RuntimeError("module has neither parameters nor BatchNorm buffers")
+        if not named and not bufs:      # e.g. a MixedOp reduced to {none, skip_connect}: nothing to lay out
+            if self.flat is None or (device is not None and self.flat.device != torch.device(device)):
+                self.flat = torch.zeros(4, dtype=torch.float32, device=device)
+                self.bn = torch.zeros(4, dtype=torch.float32, device=device)
+                self.gflat = None
+            return self
         if self._probe is not None and self._make_probe(bufs) == self._probe:
             return self
         for p in self._params:
@@ -118,7 +122,7 @@ class FlatRegion:
     # -- gradients -------------------------------------------------------
     def ensure_grads(self):
         """Make every p.grad a view of one flat buffer (zero-filled where it was unset); return the buffer."""
-        self.ensure()
+        self.ensure(self.flat.device if self.flat is not None else None)
         if not self._params:
             if self.gflat is None:
                 self.gflat = torch.zeros(4, dtype=torch.float32, device=self.flat.device)
@@ -160,9 +164,9 @@ class FlatRegion:
         self.gflat.zero_()
 
 
-def region_of(module, exclude=()) -> FlatRegion:
+def region_of(module, exclude=(), device=None) -> FlatRegion:
     r = module.__dict__.get("_gnas_region")
     if r is None:
         r = FlatRegion(module, exclude)
         module.__dict__["_gnas_region"] = r
-    return r.ensure()
+    return r.ensure(device)

@@ -1,0 +1,107 @@
+"""Edge cases of the hot path (SURVEY.md section 4 iv): ragged batch sizes, odd lengths (125 -> 42 with stride 3),
+single-candidate edges, skip-connect dropout (P-DARTS), against the CPU oracle in fp64."""
+import pytest
+import torch
+
+import genomenas_oracle as O
+from conftest import leaf, relerr
+
+import genome_nas_b200 as G
+
+
+def _shapes(module, prefix):
+    kinds = {"running_mean": "rm", "running_var": "rv", "num_batches_tracked": "nbt"}
+    return {prefix + k: (tuple(v.shape), next((t for s, t in kinds.items() if k.endswith(s)), "w"))
+            for k, v in module.state_dict().items()}
+
+
+def _oracle_mixed(m, x, w, switch, stride, P, skip_mask=None, p=0.0):
+    Q = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in P.items()}
+    xo, wo = x.double().clone().requires_grad_(True), w.double().clone().requires_grad_(True)
+    y = O.mixed_op(xo, wo, switch, stride, Q, "cell_ops.0", True, O.Recorder(), p,
+                   {"cell_ops.0": skip_mask.double()} if skip_mask is not None else None)
+    return y, xo, wo, Q
+
+
+@pytest.mark.parametrize("B,C,L,stride,switch", [
+    (1, 8, 17, 1, [True] * 9),                                   # single row, L smaller than any tile
+    (5, 8, 125, 3, [True] * 9),                                  # 125 -> 42 (cell 5), ragged batch
+    (9, 16, 43, 2, [True] * 9),                                  # odd length, batch not a multiple of 8
+    (3, 8, 30, 1, [False, False, False, False, False, False, False, False, True]),   # conv_15 only
+    (3, 8, 30, 2, [False, False, False, True, False, False, False, False, False]),   # strided skip only
+    (4, 8, 64, 1, [True, False, False, True, False, False, False, False, False]),    # none + identity
+    (2, 32, 250, 1, [False, True, True, False, True, False, False, True, False]),
+])
+def test_mixedop_shapes(backend, B, C, L, stride, switch):
+    torch.manual_seed(B * 100 + L)
+    m = G.MixedOp(C, stride, switch, 0.0)
+    P = O.synthetic_params(_shapes(m, "cell_ops.0."), 5)
+    m.load_state_dict({k[len("cell_ops.0."):]: v for k, v in P.items()})
+    m.to(backend).train()
+    x0 = torch.randn(B, C, L)
+    w0 = torch.softmax(torch.randn(sum(switch)), 0)
+    x, w = leaf(x0, backend), leaf(w0, backend)
+    y = m(x, w)
+    gy = torch.randn(y.shape)
+    (y * gy.to(backend)).sum().backward()
+    yo, xo, wo, Q = _oracle_mixed(m, x0, w0, switch, stride, P)
+    (yo * gy.double()).sum().backward()
+    assert y.shape == yo.shape
+    assert relerr(y, yo) < 1e-5
+    assert relerr(x.grad, xo.grad) < 5e-5
+    assert relerr(w.grad, wo.grad) < 5e-5
+    for n, p in m.named_parameters():
+        assert relerr(p.grad, Q["cell_ops.0." + n].grad) < 5e-5, n
+
+
+def test_skip_connect_dropout_pdarts(backend):
+    """P-DARTS: Identity -> Dropout(p) (model_discCNN.py:60-61).  The mask is drawn by the module; the kernels
+    must apply exactly that mask in forward, dX and dmix."""
+    switch = [True, True, False, True, False, True, False, False, False]
+    m = G.MixedOp(8, 1, switch, 0.3)
+    assert isinstance(m.m_ops.skip_connect, torch.nn.Sequential) and m.m_ops.skip_connect[1].p == 0.3
+    P = O.synthetic_params(_shapes(m, "cell_ops.0."), 6)
+    m.load_state_dict({k[len("cell_ops.0."):]: v for k, v in P.items()})
+    m.to(backend).train()
+    x0, w0 = torch.randn(4, 8, 50), torch.softmax(torch.randn(4), 0)
+    x, w = leaf(x0, backend), leaf(w0, backend)
+    captured = {}
+    orig = m._draw_skip_masks
+
+    def spy(desc, like):
+        masks, arr = orig(desc, like)
+        captured["mask"] = masks[0].detach().cpu().clone()
+        return masks, arr
+
+    m._draw_skip_masks = spy
+    y = m(x, w)
+    gy = torch.randn(y.shape)
+    (y * gy.to(backend)).sum().backward()
+    mask = captured["mask"]
+    assert all(v == 0.0 or abs(v - 1 / 0.7) < 1e-6 for v in torch.unique(mask).tolist())
+    assert 0.1 < float((mask == 0).float().mean()) < 0.5
+    yo, xo, wo, _ = _oracle_mixed(m, x0, w0, switch, 1, P, mask, 0.3)
+    (yo * gy.double()).sum().backward()
+    assert relerr(y, yo) < 1e-5 and relerr(x.grad, xo.grad) < 5e-5 and relerr(w.grad, wo.grad) < 5e-5
+    m.p = 0.1
+    m.update_p()
+    assert m.m_ops.skip_connect[1].p == 0.1
+
+
+def test_gradient_accumulation_semantics(backend):
+    """Two backward passes without zeroing accumulate into p.grad like autograd does."""
+    sw = [True] * 9
+    m = G.MixedOp(8, 2, sw, 0.0)
+    P = O.synthetic_params(_shapes(m, "cell_ops.0."), 7)
+    m.load_state_dict({k[len("cell_ops.0."):]: v for k, v in P.items()})
+    m.to(backend).train()
+    x, w = torch.randn(2, 8, 40, device=backend), torch.softmax(torch.randn(9, device=backend), 0)
+    m(x, w).sum().backward()
+    once = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m(x, w).sum().backward()
+    for n, p in m.named_parameters():
+        assert relerr(p.grad, 2 * once[n]) < 1e-5, n
+    m.zero_grad(set_to_none=True)
+    m(x, w).sum().backward()
+    for n, p in m.named_parameters():
+        assert relerr(p.grad, once[n]) < 1e-5, n
