@@ -437,7 +437,7 @@ struct DwBwdJob {
   float* dwd;                        // [C][K] atomics, or null
   int Lin, Lo, tin, omode;
 };
-struct DwBwdBatch { int n, B, C, pad, Wx, Wd; DwBwdJob j[kMaxDw]; };
+struct DwBwdBatch { int n, B, C, pad, Wx, Wd, RPW; DwBwdJob j[kMaxDw]; };
 
 // CTA: channel c, 8 batch rows (one per warp).  Stride 1 (all but the first conv of strided edges): every lane
 // produces 4 consecutive positions from register windows (128-bit shared loads, static tap indices).
@@ -445,8 +445,6 @@ template <int K, int D, int S>
 __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwBwdBatch P) {
   const DwBwdJob& J = P.j[blockIdx.z];
   const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y * 8 + warp;
-  const bool ok = b < P.B;
   // every depthwise candidate of the reference pads by (K-1)*D/2 (operations_14_9.py:24-28)
   constexpr int PADC = (K - 1) * D / 2;
   // du row: index i <-> l = i - OFF, OFF a multiple of 4 >= PADC, so that windows start 16-byte aligned
@@ -457,7 +455,19 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
   __shared__ float red[8][K + 2];
   float mean = 0.f, rstd = 1.f;
   if (J.tin >= T_BN_RELU) { mean = J.in_stat[c]; rstd = J.in_stat[P.C + c]; }
+  float w[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) w[t] = J.wd[c * K + t];
+  float s = 0.f, qq = 0.f;
+  float gw[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) gw[t] = 0.f;
+  // each warp walks RPW batch rows of channel c and reduces its weight-gradient / BN sums once at the end
+  for (int r = 0; r < P.RPW; ++r) {
+  const int b = (blockIdx.y * P.RPW + r) * 8 + warp;
+  const bool ok = b < P.B;
   const float* xg = J.x + (long long)(ok ? b : 0) * J.xbs + (long long)c * J.Lin;
+  __syncwarp();
   if (ok) {
     for (int p = lane; p < P.Wx; p += 32) {
       const int pos = p - P.pad;
@@ -470,13 +480,6 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
     }
   }
   __syncwarp();
-  float w[K];
-#pragma unroll
-  for (int t = 0; t < K; ++t) w[t] = J.wd[c * K + t];
-  float s = 0.f, qq = 0.f;
-  float gw[K];
-#pragma unroll
-  for (int t = 0; t < K; ++t) gw[t] = 0.f;
   if (ok) {
     float* orow = J.out + (long long)b * J.obs + (long long)c * J.Lin;
     if (S == 1) {
@@ -544,6 +547,7 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
       }
     }
   }
+  }   // rows
 #pragma unroll
   for (int t = 0; t < K; ++t) { gw[t] = warp_sum(gw[t]); if (lane == 0) red[warp][t] = gw[t]; }
   s = warp_sum(s); qq = warp_sum(qq);

@@ -31,7 +31,7 @@ static inline int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b
 static inline int choose_kc(int kw, const int* cins, int n, int cout, int wp) {
   int g = cins[0];
   for (int i = 1; i < n; ++i) g = gcd_int(g, cins[i]);
-  if (kw != 1) { int kc = 8; while (g % kc) kc >>= 1; return kc; }
+  if (kw != 1) { int kc = cout > 64 ? 4 : 8; while (g % kc) kc >>= 1; return kc; }   // <= 32 KB of weights per chunk
   int kc = g;
   while (kc > 8 && kc % 2 == 0 && sizeof(float) * ((size_t)kc * wp + (size_t)kc * cout) > 96 * 1024) kc /= 2;
   return kc;
@@ -157,7 +157,7 @@ static inline int pick_tc(int a, int b) {
   return 1;
 }
 // CTAs per launch to aim for when splitting the position range of a weight-gradient job
-constexpr int kWgradTargetCtas = 4 * 148;
+constexpr int kWgradTargetCtas = 2 * 148;
 
 template <int TC>
 static void launch_pw_wgrad_t(WgBatch& b, int nblk, int ny, cudaStream_t st) {
@@ -258,7 +258,11 @@ static void launch_dw_bwd_t(DwBwdBatch& b, cudaStream_t st) {
   b.Wx = round_up(wx, 4); b.Wd = round_up(wd, 4);
   const size_t smem = sizeof(float) * 8 * (size_t)(b.Wx + b.Wd);
   GNAS_PREP_SMEM((k_dw_bwd<K, D, S>), smem);
-  dim3 grid(b.C, cdiv(b.B, 8), b.n);
+  // rows per warp: keep >= ~2 CTAs per SM, reduce the per-row reduction/atomic overhead when rows are short
+  int rpw = (b.C * cdiv(b.B, 8) * b.n) / (2 * 148);
+  rpw = rpw < 1 ? 1 : (rpw > 8 ? 8 : rpw);
+  b.RPW = rpw;
+  dim3 grid(b.C, cdiv(b.B, 8 * rpw), b.n);
   GNAS_LAUNCH((k_dw_bwd<K, D, S>), grid, dim3(kThreads), smem, st, b);
 }
 static int launch_dw_bwd(int K, int D, int S, DwBwdBatch& b, cudaStream_t st) {

@@ -194,6 +194,29 @@ __device__ __forceinline__ int rhn_ks(int BP, int N) {
 
 constexpr int kStages = 4;    // cp.async ring depth of the streamed operand
 
+// one kKCH-row chunk of the register-tiled product: 4 batch rows x 4 columns per thread, every KS-th k.
+// Compile-time trip count + explicit one-deep software pipeline so the shared loads of step i+1 are in
+// flight while the 16 FMAs of step i issue (only 2 warps per scheduler are resident).
+template <int KS>
+__device__ __forceinline__ void rhn_chunk(const float* __restrict__ as, const float* __restrict__ wk, int BP, float (&acc)[4][4]) {
+  constexpr int NK = kKCH / KS;
+  float4 a[2], w[2];
+  a[0] = *reinterpret_cast<const float4*>(as);
+  w[0] = *reinterpret_cast<const float4*>(wk);
+#pragma unroll
+  for (int i = 0; i < NK; ++i) {
+    if (i + 1 < NK) {
+      a[(i + 1) & 1] = *reinterpret_cast<const float4*>(as + (size_t)(i + 1) * KS * BP);
+      w[(i + 1) & 1] = *reinterpret_cast<const float4*>(wk + (i + 1) * KS * 8);
+    }
+    const float4 x = a[i & 1], y = w[i & 1];
+    acc[0][0] = fmaf(x.x, y.x, acc[0][0]); acc[0][1] = fmaf(x.x, y.y, acc[0][1]); acc[0][2] = fmaf(x.x, y.z, acc[0][2]); acc[0][3] = fmaf(x.x, y.w, acc[0][3]);
+    acc[1][0] = fmaf(x.y, y.x, acc[1][0]); acc[1][1] = fmaf(x.y, y.y, acc[1][1]); acc[1][2] = fmaf(x.y, y.z, acc[1][2]); acc[1][3] = fmaf(x.y, y.w, acc[1][3]);
+    acc[2][0] = fmaf(x.z, y.x, acc[2][0]); acc[2][1] = fmaf(x.z, y.y, acc[2][1]); acc[2][2] = fmaf(x.z, y.z, acc[2][2]); acc[2][3] = fmaf(x.z, y.w, acc[2][3]);
+    acc[3][0] = fmaf(x.w, y.x, acc[3][0]); acc[3][1] = fmaf(x.w, y.y, acc[3][1]); acc[3][2] = fmaf(x.w, y.z, acc[3][2]); acc[3][3] = fmaf(x.w, y.w, acc[3][3]);
+  }
+}
+
 // C[m][n] partial = sum_k A[k][m] * W[k][n]; A ([K][BP], already masked) is streamed from global/L2 through a
 // kStages-deep cp.async ring of kKCH-row chunks (one __syncthreads per chunk); the W slices are resident in
 // shared memory.  The K-split partials are left in `part`, which ALIASES the ring (safe: written after the
@@ -231,25 +254,24 @@ __device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const flo
     __syncthreads();                     // ... for everyone's; and everyone is done with chunk c-1
     issue(c + kStages - 1);              // refill the slot chunk c-1 occupied
     if (active) {
-      const float* as = abuf + (c % kStages) * kKCH * BP + rg * 4;
-      const float* wk = wcol + (size_t)(c * kKCH) * 8;
-#pragma unroll 4
-      for (int k = ks; k < kKCH; k += KS) {
-        const float4 a = *reinterpret_cast<const float4*>(as + k * BP);
-        const float4 w = *reinterpret_cast<const float4*>(wk + k * 8);
-        acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]); acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
-        acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]); acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
-        acc[2][0] = fmaf(a.z, w.x, acc[2][0]); acc[2][1] = fmaf(a.z, w.y, acc[2][1]); acc[2][2] = fmaf(a.z, w.z, acc[2][2]); acc[2][3] = fmaf(a.z, w.w, acc[2][3]);
-        acc[3][0] = fmaf(a.w, w.x, acc[3][0]); acc[3][1] = fmaf(a.w, w.y, acc[3][1]); acc[3][2] = fmaf(a.w, w.z, acc[3][2]); acc[3][3] = fmaf(a.w, w.w, acc[3][3]);
+      const float* as = abuf + (c % kStages) * kKCH * BP + rg * 4 + ks * BP;
+      const float* wk = wcol + (size_t)(c * kKCH + ks) * 8;
+      switch (KS) {
+        case 1: rhn_chunk<1>(as, wk, BP, acc); break;
+        case 2: rhn_chunk<2>(as, wk, BP, acc); break;
+        case 4: rhn_chunk<4>(as, wk, BP, acc); break;
+        default: rhn_chunk<8>(as, wk, BP, acc); break;
       }
     }
   }
   cp_async_wait<0>();
   __syncthreads();                       // ring no longer read: `part` may overwrite it
+  // partials are stored column-major ([ks][n][BP], 4 consecutive batch rows per 128-bit store): conflict-free
+  // for these stores and for the batch-row-fastest reads of the elementwise phase
   if (active) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-      *reinterpret_cast<float4*>(part + ((size_t)(ks * BP + rg * 4 + a)) * N + cg * 4) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    for (int b = 0; b < 4; ++b)
+      *reinterpret_cast<float4*>(part + ((size_t)(ks * N + cg * 4 + b)) * BP + rg * 4) = make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
   }
   __syncthreads();
 }
@@ -350,8 +372,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
     const int p = i * (i + 1) / 2 + j;
     float c = 0.f, h = 0.f;
     for (int s = 0; s < KS; ++s) {
-      c += part[(size_t)(s * BP + m) * N + irel * 8 + col];
-      h += part[(size_t)(s * BP + m) * N + irel * 8 + 4 + col];
+      c += part[(size_t)(s * N + irel * 8 + col) * BP + m];
+      h += part[(size_t)(s * N + irel * 8 + 4 + col) * BP + m];
     }
     if (store) {
       float* chp = P.CHT + (((size_t)t * 36 + p) * 2) * HB + (size_t)(n0 + col) * BP + m;
@@ -379,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
       for (int i = tid; i < B * 4; i += kThreads) {
         const int col = i / B, m = i - col * B;
         float c = 0.f, h = 0.f;
-        for (int s = 0; s < KS; ++s) { c += part[(size_t)(s * BP + m) * 8 + col]; h += part[(size_t)(s * BP + m) * 8 + 4 + col]; }
+        for (int s = 0; s < KS; ++s) { c += part[(size_t)(s * 8 + col) * BP + m]; h += part[(size_t)(s * 8 + 4 + col) * BP + m]; }
         P.C0T[((size_t)t * 2 + 0) * HB + (size_t)(n0 + col) * BP + m] = c;
         P.C0T[((size_t)t * 2 + 1) * HB + (size_t)(n0 + col) * BP + m] = h;
         const float hp = hloc[m * 4 + col];
@@ -422,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
       for (int it = tid; it < 4 * B; it += kThreads) {        // pre-activations of edge (j, j)
         const int m = it % B, col = it / B;
         float c = 0.f, h = 0.f;
-        for (int s = 0; s < KS; ++s) { c += part[(size_t)(s * BP + m) * N + col]; h += part[(size_t)(s * BP + m) * N + 4 + col]; }
+        for (int s = 0; s < KS; ++s) { c += part[(size_t)(s * N + col) * BP + m]; h += part[(size_t)(s * N + 4 + col) * BP + m]; }
         float* chp = P.CHT + (((size_t)t * 36 + j * (j + 1) / 2 + j) * 2) * HB + (size_t)(n0 + col) * BP + m;
         chp[0] = c; chp[HB] = h;
       }
