@@ -49,8 +49,10 @@ static __global__ void __launch_bounds__(kThreads) k_bwd_reduce(const __grid_con
       const float* zr = T.z + (long long)b * T.bs + (long long)c * P.L;
       if (T.mask) {
         const float* mr = T.mask + ((long long)b * P.C + c) * P.L;
+        _Pragma("unroll 4")
         for (int l = lane; l < P.L; l += 32) s2 = fmaf(gr[l], zr[l] * mr[l], s2);
       } else {
+        _Pragma("unroll 4")
         for (int l = lane; l < P.L; l += 32) s2 = fmaf(gr[l], zr[l], s2);
       }
     }
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(kThreads) k_dense_bwd_dx(const __grid_constant
       const float* zr = J.z ? J.z + (long long)b * J.zbs + (long long)(c0 + co) * J.Lo : nullptr;
       float A = 1.f, Bz = 0.f, D = 0.f;
       if (zr) { A = J.coef[c0 + co]; Bz = J.coef[J.Cout + c0 + co]; D = J.coef[2 * J.Cout + c0 + co]; }
+      _Pragma("unroll 4")
       for (int p = lane; p < Wp; p += 32) {
         const int l = lbase + p;
         float v = 0.f;
@@ -217,18 +220,26 @@ __global__ void __launch_bounds__(kThreads) k_dense_bwd_dx(const __grid_constant
       float* orow = J.out + (long long)b * J.obs + (long long)ci * J.Lin;
       const float* xrow = J.xin ? J.xin + (long long)b * J.xibs + (long long)ci * J.Lin : nullptr;
       const float mean = (J.omode == O_BNRELU_STORE) ? J.xin_stat[ci] : 0.f;
+      // all loads first (they are independent; interleaving them with the stores would serialise on aliasing)
+      float xv[4], ov[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int pos = m0 + S * (4 * q + n) + rho;
+        const bool in = pos < J.Lin;
+        xv[n] = (in && xrow) ? xrow[pos] : 0.f;
+        ov[n] = (in && (J.omode == O_ACC || J.omode == O_RELU_ACC)) ? orow[pos] : 0.f;
+      }
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         const int pos = m0 + S * (4 * q + n) + rho;
         if (pos < J.Lin) {
           const float v = acc[m][n];
           if (J.omode == O_STORE) orow[pos] = v;
-          else if (J.omode == O_ACC) orow[pos] += v;
-          else if (J.omode == O_RELU_ACC) { if (xrow[pos] > 0.f) orow[pos] += v; }
+          else if (J.omode == O_ACC) orow[pos] = ov[n] + v;
+          else if (J.omode == O_RELU_ACC) { if (xv[n] > 0.f) orow[pos] = ov[n] + v; }
           else {
-            const float zi = xrow[pos];
-            const float vv = zi > mean ? v : 0.f;
-            orow[pos] = vv; s += vv; qq = fmaf(vv, zi, qq);
+            const float vv = xv[n] > mean ? v : 0.f;
+            orow[pos] = vv; s += vv; qq = fmaf(vv, xv[n], qq);
           }
         }
       }
@@ -300,8 +311,10 @@ __global__ void __launch_bounds__(kThreads) k_pw_wgrad(const __grid_constant__ W
       if (J.z) {
         const float* zr = J.z + (long long)b * J.zbs + (long long)(co0 + c) * J.Lo + l0;
         const float A = J.coef[co0 + c], Bz = J.coef[P.Cout + co0 + c], D = J.coef[2 * P.Cout + co0 + c];
+        _Pragma("unroll 4")
         for (int l = lane; l < TL; l += 32) dzs[l * po + c] = l < nl ? fmaf(A, gr[l], fmaf(Bz, zr[l], D)) : 0.f;
       } else {
+        _Pragma("unroll 4")
         for (int l = lane; l < TL; l += 32) dzs[l * po + c] = l < nl ? gr[l] : 0.f;
       }
     }
@@ -309,6 +322,7 @@ __global__ void __launch_bounds__(kThreads) k_pw_wgrad(const __grid_constant__ W
       const float* rr = J.r + (long long)b * J.rbs + (long long)(ci0 + c) * J.Lin + (long long)l0 * P.S;
       float mean = 0.f, rstd = 1.f;
       if (J.tin >= T_BN_RELU) { mean = J.r_stat[ci0 + c]; rstd = J.r_stat[J.Cin + ci0 + c]; }
+      _Pragma("unroll 4")
       for (int l = lane; l < TL; l += 32) rs[l * pi + c] = l < nl ? apply_tin(rr[l * P.S], J.tin, mean, rstd) : 0.f;
     }
     __syncthreads();
@@ -361,11 +375,11 @@ __global__ void __launch_bounds__(kThreads) k_conv_wgrad(const __grid_constant__
   const int grp = tid / per, r2 = tid - grp * per;
   const int coq = r2 / cib, ci = r2 - coq * cib;
   const bool active = grp < G;
-  const int TLg = P.TL;                 // positions per group per tile
+  const int TLg = P.TL;                 // positions per group per tile (multiple of 4)
   const int TLc = TLg * G;              // positions per tile
-  const int pz = TLc | 1;
+  const int pz = (TLc + 3) / 4 * 4 + 4;  // multiple of 4: 128-bit (warp-broadcast) loads of dz
   const int Wr = (TLc - 1) * S + KW;
-  const int pr = Wr | 1;
+  const int pr = Wr | 1;                // odd: lanes (= input channels) hit distinct banks
   GNAS_DYN_SMEM(float, smem);
   float* dzs = smem;                    // [cob][pz]
   float* rs = dzs + cob * pz;           // [cib][pr]
@@ -384,8 +398,10 @@ __global__ void __launch_bounds__(kThreads) k_conv_wgrad(const __grid_constant__
       if (J.z) {
         const float* zr = J.z + (long long)b * J.zbs + (long long)(co0 + c) * J.Lo + l0;
         const float A = J.coef[co0 + c], Bz = J.coef[P.Cout + co0 + c], D = J.coef[2 * P.Cout + co0 + c];
+        _Pragma("unroll 4")
         for (int l = lane; l < TLc; l += 32) dzs[c * pz + l] = l < nl ? fmaf(A, gr[l], fmaf(Bz, zr[l], D)) : 0.f;
       } else {
+        _Pragma("unroll 4")
         for (int l = lane; l < TLc; l += 32) dzs[c * pz + l] = l < nl ? gr[l] : 0.f;
       }
     }
@@ -394,6 +410,7 @@ __global__ void __launch_bounds__(kThreads) k_conv_wgrad(const __grid_constant__
       const float* rr = J.r + (long long)b * J.rbs + (long long)(ci0 + c) * J.Lin;
       float mean = 0.f, rstd = 1.f;
       if (J.tin >= T_BN_RELU) { mean = J.r_stat[ci0 + c]; rstd = J.r_stat[J.Cin + ci0 + c]; }
+      _Pragma("unroll 4")
       for (int p = lane; p < Wr; p += 32) {
         const int pos = in0 + p;
         rs[c * pr + p] = (pos >= 0 && pos < J.Lin) ? apply_tin(rr[pos], J.tin, mean, rstd) : 0.f;
@@ -401,18 +418,30 @@ __global__ void __launch_bounds__(kThreads) k_conv_wgrad(const __grid_constant__
     }
     __syncthreads();
     if (active) {
+      // 4 positions per step: 4 x 128-bit dz loads (broadcast) + one (3S+KW)-wide window of r -> 16*KW FMAs
+      constexpr int NXW = 3 * S + KW;
       const int le = min(nl, (grp + 1) * TLg);
       const float* rr = rs + ci * pr;
       const float* dz0 = dzs + (coq * 4) * pz;
-      for (int l = grp * TLg; l < le; ++l) {
-        const float d0 = dz0[l], d1 = dz0[pz + l], d2 = dz0[2 * pz + l], d3 = dz0[3 * pz + l];
+      for (int l = grp * TLg; l < le; l += 4) {
+        float d[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(dz0 + i * pz + l);
+          d[i][0] = v.x; d[i][1] = v.y; d[i][2] = v.z; d[i][3] = v.w;
+        }
+        float rw[NXW];
         const float* rl = rr + l * S;
 #pragma unroll
-        for (int t = 0; t < KW; ++t) {
-          const float rv = rl[t];
-          acc[0][t] = fmaf(d0, rv, acc[0][t]); acc[1][t] = fmaf(d1, rv, acc[1][t]);
-          acc[2][t] = fmaf(d2, rv, acc[2][t]); acc[3][t] = fmaf(d3, rv, acc[3][t]);
-        }
+        for (int k = 0; k < NXW; ++k) rw[k] = rl[k];
+#pragma unroll
+        for (int t = 0; t < KW; ++t)
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const float rv = rw[n * S + t];
+            acc[0][t] = fmaf(d[0][n], rv, acc[0][t]); acc[1][t] = fmaf(d[1][n], rv, acc[1][t]);
+            acc[2][t] = fmaf(d[2][n], rv, acc[2][t]); acc[3][t] = fmaf(d[3][n], rv, acc[3][t]);
+          }
       }
     }
     __syncthreads();
@@ -469,11 +498,13 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
   const float* xg = J.x + (long long)(ok ? b : 0) * J.xbs + (long long)c * J.Lin;
   __syncwarp();
   if (ok) {
+    _Pragma("unroll 4")
     for (int p = lane; p < P.Wx; p += 32) {
       const int pos = p - P.pad;
       xrow[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xg[pos], J.tin, mean, rstd) : 0.f;
     }
     const float* dg = J.du + (long long)b * J.dubs + (long long)c * J.Lo;
+    _Pragma("unroll 4")
     for (int i = lane; i < P.Wd; i += 32) {
       const int l = i - OFF;
       drow[i] = (l >= 0 && l < J.Lo) ? dg[l] : 0.f;
@@ -498,13 +529,19 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
         for (int t = 0; t < K; ++t)
 #pragma unroll
           for (int n = 0; n < 4; ++n) a[n] = fmaf(w[t], dw_[SH + n + (K - 1 - t) * D], a[n]);
+        float xv[4], ov[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const bool in = m0 + n < J.Lin;
+          xv[n] = in ? xg[m0 + n] : 0.f;
+          ov[n] = (in && J.omode == O_RELU_ACC) ? orow[m0 + n] : 0.f;
+        }
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
           const int m = m0 + n;
           if (m < J.Lin) {
-            const float xv = xg[m];
-            if (J.omode == O_RELU_ACC) { if (xv > 0.f) orow[m] += a[n]; }
-            else { const float v = xv > mean ? a[n] : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv, qq); }
+            if (J.omode == O_RELU_ACC) { if (xv[n] > 0.f) orow[m] = ov[n] + a[n]; }
+            else { const float v = xv[n] > mean ? a[n] : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv[n], qq); }
           }
         }
       }
@@ -527,6 +564,7 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
         }
       }
     } else {
+      _Pragma("unroll 4")
       for (int m = lane; m < J.Lin; m += 32) {
         float a = 0.f;
 #pragma unroll
@@ -539,6 +577,7 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
         else { const float v = xv > mean ? a : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv, qq); }
       }
       if (J.dwd) {
+        _Pragma("unroll 4")
         for (int l = lane; l < J.Lo; l += 32) {
           const float dv = drow[l + OFF];
 #pragma unroll
@@ -585,11 +624,13 @@ static __global__ void __launch_bounds__(kThreads) k_pool_bwd(const __grid_const
   const int S = P.S;
   const float* xg = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
   const float* gg = J.g + (long long)b * J.gbs + (long long)c * J.Lo;
+  _Pragma("unroll 4")
   for (int p = lane; p < P.Wx; p += 32) {
     const int pos = p - 2;
     xrow[p] = (pos >= 0 && pos < J.Lin) ? xg[pos] : -INFINITY;
   }
   const long long zo = ((long long)b * P.C + c) * J.Lo;
+  _Pragma("unroll 4")
   for (int i = lane; i < P.Wd; i += 32) {
     const int l = i - 4;
     float vm = 0.f, va = 0.f;
@@ -606,6 +647,7 @@ static __global__ void __launch_bounds__(kThreads) k_pool_bwd(const __grid_const
   __syncwarp();
   const float wskip = J.skip_widx >= 0 ? P.mixw[J.skip_widx] : 0.f;
   float* drow = J.dx + (long long)b * J.dxbs + (long long)c * J.Lin;
+  _Pragma("unroll 4")
   for (int m = lane; m < J.Lin; m += 32) {
     float a = 0.f;
     // windows l with l*S-2 <= m <= l*S+2

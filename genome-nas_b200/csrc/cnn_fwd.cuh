@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kThreads) k_dense_fwd(const __grid_constant__ 
       const float* xr = xb + (long long)(c0 + ci) * J.Lin;
       float mean = 0.f, rstd = 1.f;
       if (J.tin >= T_BN_RELU) { mean = J.in_stat[c0 + ci]; rstd = J.in_stat[J.Cin + c0 + ci]; }
+      _Pragma("unroll 4")
       for (int p = lane; p < Wp; p += 32) {
         const int pos = in0 + p;
         float v = 0.f;
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwB
     const float* xr = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
     float mean = 0.f, rstd = 1.f;
     if (J.tin >= T_BN_RELU) { mean = J.in_stat[c]; rstd = J.in_stat[P.C + c]; }
+    _Pragma("unroll 4")
     for (int p = lane; p < P.Wp; p += 32) {
       const int pos = p - P.pad;
       row[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xr[pos], J.tin, mean, rstd) : 0.f;
@@ -223,6 +225,7 @@ static __global__ void __launch_bounds__(kThreads) k_pool_fwd(const __grid_const
   if (b < P.B) {
     const float* xr = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
     const long long o = ((long long)b * P.C + c) * J.Lout;
+    _Pragma("unroll 4")
     for (int l = lane; l < J.Lout; l += 32) {
       const int s0 = l * P.S - 2;
       float mx = -INFINITY, sum = 0.f;

@@ -69,6 +69,15 @@ __device__ __forceinline__ float apply_tin(float v, int tin, float mean, float r
   return v;
 }
 
+// 128-bit reduction into global memory (one L2 atomic transaction instead of four; sm_90+)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+#ifdef GNAS_EMUL
+  atomicAdd(addr, a); atomicAdd(addr + 1, b); atomicAdd(addr + 2, c); atomicAdd(addr + 3, d);
+#else
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+#endif
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

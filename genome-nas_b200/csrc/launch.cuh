@@ -203,10 +203,12 @@ static void launch_conv_wgrad_t(WgBatch& b, int nblk, int Lo, cudaStream_t st) {
   int tlg = 512 / G;
   tlg = tlg > 64 ? 64 : (tlg < 16 ? 16 : tlg);
   while (tlg > 16 && tlg * G >= 2 * Lo) tlg /= 2;     // short rows: do not pad a tile to twice the row
+  tlg &= ~3;                                          // groups start on 16-byte boundaries of the dz rows
   b.TL = tlg;
   const int TLc = tlg * G;
-  const int pz = TLc | 1, pr = ((TLc - 1) * S + KW) | 1;
-  const size_t smem = sizeof(float) * ((size_t)b.COB * pz + (size_t)b.CIB * pr);
+  // r rows are read up to 3*S past the last used window element (4-position steps): keep a small tail
+  const int pz = round_up(TLc, 4) + 4, pr = ((TLc - 1) * S + KW) | 1;
+  const size_t smem = sizeof(float) * ((size_t)b.COB * pz + (size_t)b.CIB * pr + 4 * S + 8);
   GNAS_PREP_SMEM((k_conv_wgrad<KW, S>), smem);
   const int tiles = b.B * cdiv(Lo, TLc);
   int tpc = (int)((long long)tiles * nblk * b.n / kWgradTargetCtas);
@@ -259,8 +261,8 @@ static void launch_dw_bwd_t(DwBwdBatch& b, cudaStream_t st) {
   const size_t smem = sizeof(float) * 8 * (size_t)(b.Wx + b.Wd);
   GNAS_PREP_SMEM((k_dw_bwd<K, D, S>), smem);
   // rows per warp: keep >= ~2 CTAs per SM, reduce the per-row reduction/atomic overhead when rows are short
-  int rpw = (b.C * cdiv(b.B, 8) * b.n) / (2 * 148);
-  rpw = rpw < 1 ? 1 : (rpw > 8 ? 8 : rpw);
+  int rpw = (b.C * cdiv(b.B, 8) * b.n) / (16 * 148);      // only when the grid is far larger than the machine
+  rpw = rpw < 1 ? 1 : (rpw > 2 ? 2 : rpw);
   b.RPW = rpw;
   dim3 grid(b.C, cdiv(b.B, 8 * rpw), b.n);
   GNAS_LAUNCH((k_dw_bwd<K, D, S>), grid, dim3(kThreads), smem, st, b);

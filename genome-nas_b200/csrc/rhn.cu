@@ -19,6 +19,7 @@ namespace gnas {
 constexpr int kNC = 4;        // hidden columns per CTA in the persistent forward kernel
 constexpr int kKCH = 32;      // K rows per shared-memory chunk
 constexpr int kMaxBP = 64;    // padded batch rows supported by the persistent kernel
+constexpr int kRhnThreads = 512;   // persistent forward CTA: 16 warps hide the shared-memory latency of the register-tiled product
 
 #ifdef GNAS_EMUL
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
@@ -67,7 +68,7 @@ struct RhnTable {             // per edge p = i(i+1)/2 + j: index into probs for
 struct RhnPlan {
   int BP;
   long long xmT, xkT, hmT, h0T, ring, ST, CHT, C0T, HT, stat, bar, fwd_total;   // forward workspace (floats)
-  long long dsT, dhT, dxT, doT, dpacc, bwd_total;                              // backward scratch
+  long long dsT, dhT, dxT, doT, dpacc, WsT, W0T, bwd_zero, bwd_total;           // backward scratch
 };
 
 static RhnPlan rhn_plan(const GnasRhnDesc* d) {
@@ -86,13 +87,16 @@ static RhnPlan rhn_plan(const GnasRhnDesc* d) {
   p.C0T = o; o += T * 2 * HB;
   p.HT = o; o += T * HB;           // h_t^T
   p.stat = o; o += T * 9 * 2 * H;
-  p.bar = o; o += 64;              // barrier counter + abort flag
+  p.bar = o; o += 256;             // barrier counter + abort flag (+ debug timing marks)
   p.fwd_total = o;
   o = 0;
   p.dpacc = o; o += 2 * 36 * 4;    // doubles
   p.dsT = o; o += 9 * HB;
   p.dhT = o; o += 2 * HB;          // ping-pong
   p.dxT = o; o += T * HB;
+  p.bwd_zero = o;                  // everything above is zero-initialised per call
+  p.WsT = o; o += 8 * H * 2 * H;   // Ws[i]^T  [2H][H]  (so that GEMM tiles are straight 16-byte copies)
+  p.W0T = o; o += 2 * H * 2 * H;   // W0^T     [2H][2H]
   p.bwd_total = o;
   return p;
 }
@@ -186,10 +190,10 @@ __device__ __forceinline__ bool grid_wait(unsigned* bar, int* abort_flag, unsign
 
 // K-split factor: power of two, fills the CTA, and keeps KS * N <= 64 columns of the partial buffer
 __device__ __forceinline__ int rhn_ks(int BP, int N) {
-  int a = kThreads / ((BP / 4) * (N / 4));
-  const int b = 64 / N;
+  int a = kRhnThreads / ((BP / 4) * (N / 4));
+  const int b = 128 / N;                 // partial buffer = the ring: kStages*kKCH*BP = 128*BP floats
   a = a < b ? a : b;
-  return a >= 8 ? 8 : (a >= 4 ? 4 : (a >= 2 ? 2 : 1));
+  return a >= 16 ? 16 : (a >= 8 ? 8 : (a >= 4 ? 4 : (a >= 2 ? 2 : 1)));
 }
 
 constexpr int kStages = 4;    // cp.async ring depth of the streamed operand
@@ -243,7 +247,7 @@ __device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const flo
       float* dst = abuf + (c % kStages) * kKCH * BP;
       const int k0 = c * kKCH;
       const float* src = (k0 < K0) ? A0 + (size_t)k0 * BP : A1 + (size_t)(k0 - K0) * BP;
-      for (int i = tid; i < f4_per_chunk; i += kThreads) cp_async16(dst + 4 * i, src + 4 * i);
+      for (int i = tid; i < f4_per_chunk; i += kRhnThreads) cp_async16(dst + 4 * i, src + 4 * i);
     }
     cp_async_commit();                   // always commit (possibly empty) so that group counting stays uniform
   };
@@ -260,7 +264,8 @@ __device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const flo
         case 1: rhn_chunk<1>(as, wk, BP, acc); break;
         case 2: rhn_chunk<2>(as, wk, BP, acc); break;
         case 4: rhn_chunk<4>(as, wk, BP, acc); break;
-        default: rhn_chunk<8>(as, wk, BP, acc); break;
+        case 8: rhn_chunk<8>(as, wk, BP, acc); break;
+        default: rhn_chunk<16>(as, wk, BP, acc); break;
       }
     }
   }
@@ -276,7 +281,7 @@ __device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const flo
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_constant__ RhnFwd P) {
+__global__ void __launch_bounds__(kRhnThreads, 1) k_rhn_forward(const __grid_constant__ RhnFwd P) {
   const int H = P.H, B = P.B, BP = P.BP, T = P.T;
   const int n0 = blockIdx.x * kNC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -296,21 +301,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
   float* run = pq + 36;                       // [2][4] running mean | var of own columns
   __shared__ int s_abort;
   // ---- one-time setup: weight slices, masks, probability table
-  for (int i = tid; i < 2 * H * 8; i += kThreads) {
+  for (int i = tid; i < 2 * H * 8; i += kRhnThreads) {
     const int k = i >> 3, c = i & 7;
     W0s[i] = P.W0[(size_t)k * 2 * H + (c < 4 ? n0 + c : H + n0 + c - 4)];
   }
-  for (int i = tid; i < 8 * H * 8; i += kThreads) {
+  for (int i = tid; i < 8 * H * 8; i += kRhnThreads) {
     const int c = i & 7, k = (i >> 3) % H, w = i / (8 * H);
     Wss[i] = P.Ws[((size_t)w * H + k) * 2 * H + (c < 4 ? n0 + c : H + n0 + c - 4)];
   }
-  for (int i = tid; i < BP * 4; i += kThreads) {
+  for (int i = tid; i < BP * 4; i += kRhnThreads) {
     const int m = i >> 2, c = i & 3;
     hml[i] = P.hmT[(size_t)(n0 + c) * BP + m];
     hloc[i] = P.h0T[(size_t)(n0 + c) * BP + m];
   }
-  for (int i = tid; i < 8 * BP * 4; i += kThreads) accn[i] = 0.f;
-  for (int i = tid; i < 9 * BP * 4; i += kThreads) sloc[i] = 0.f;
+  for (int i = tid; i < 8 * BP * 4; i += kRhnThreads) accn[i] = 0.f;
+  for (int i = tid; i < 9 * BP * 4; i += kRhnThreads) sloc[i] = 0.f;
   if (tid < 36) {
     float q = 0.f;
     for (int k = 0; k < 4; ++k) {
@@ -324,6 +329,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
   __syncthreads();
   unsigned bar_target = 0;
   const float invB = 1.f / (float)B;
+#ifdef GNAS_RHN_TIMING
+  long long* dbg = reinterpret_cast<long long*>(P.bar + 16);   // [stage 0..8][4 marks] of time step 1, CTA 0
+#define GNAS_MARK(stage, k) do { if (blockIdx.x == 0 && t == 1 && tid == 0) dbg[(stage) * 4 + (k)] = clock64(); } while (0)
+#else
+#define GNAS_MARK(stage, k) do { } while (0)
+#endif
 
   // BatchNorm over the batch for the 4 own columns of `src` ([BP][4]); warp w < 4 handles column w and
   // publishes the masked state to the ring (what the other CTAs wait for).
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
   };
   // unmasked state for backward (off the critical path)
   auto stash_state = [&](int t, int stage) {
-    for (int i = tid; i < BP * 4; i += kThreads) {
+    for (int i = tid; i < BP * 4; i += kRhnThreads) {
       const int col = i / BP, m = i - col * BP;
       P.ST[((size_t)t * 9 + stage) * HB + (size_t)(n0 + col) * BP + m] = sloc[(stage * BP + m) * 4 + col];
     }
@@ -395,10 +406,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
 
   for (int t = 0; t < T; ++t) {
     // ---------------- stage 0: [c0|h0] = [x_t*xm | h*hm] W0 ; s_0 = BN(h + sig(c0)(tanh(h0) - h))
+    GNAS_MARK(0, 0);
     rhn_gemm(P.xmT + (size_t)t * HB, P.ring + 9 * HB, H, 2 * H, BP, 8, W0s, 0, true, abuf, part);
+    GNAS_MARK(0, 1);
     {
       const int KS = rhn_ks(BP, 8);
-      for (int i = tid; i < B * 4; i += kThreads) {
+      for (int i = tid; i < B * 4; i += kRhnThreads) {
         const int col = i / B, m = i - col * B;
         float c = 0.f, h = 0.f;
         for (int s = 0; s < KS; ++s) { c += part[(size_t)(s * 8 + col) * BP + m]; h += part[(size_t)(s * 8 + 4 + col) * BP + m]; }
@@ -410,24 +423,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
       __syncthreads();
       bn_publish(tmp0, t, 0);
     }
+    GNAS_MARK(0, 2);
     grid_arrive(P.bar);
     stash_state(t, 0);
     bar_target += gridDim.x;
     if (grid_wait(P.bar, P.abort_flag, bar_target, &s_abort)) return;
+    GNAS_MARK(0, 3);
     // ---------------- stages j = 0..7: multiply s_j with the slices of Ws[j..7]; node j -> s_{j+1} first
     for (int j = 0; j < 8; ++j) {
       const int N = 8 * (8 - j);
+      GNAS_MARK(j + 1, 0);
       rhn_gemm(P.ring + (size_t)j * HB, nullptr, H, H, BP, N, Wss + (size_t)j * H * 8, H * 8, false, abuf, part);
+      GNAS_MARK(j + 1, 1);
       const int KS = rhn_ks(BP, N);
       // critical: edge (j, j) completes node j
-      for (int it = tid; it < 4 * B; it += kThreads) edge_item(t, j, 0, it % B, it / B, N, KS, false);
+      for (int it = tid; it < 4 * B; it += kRhnThreads) edge_item(t, j, 0, it % B, it / B, N, KS, false);
       __syncthreads();
       bn_publish(accn + j * BP * 4, t, j + 1);
       const bool last = j == 7;
       if (last) {
         __syncthreads();
         // h_t = mean(s_1..s_8)  (model_search.py:96); its masked copy feeds stage 0 of the next step
-        for (int i = tid; i < BP * 4; i += kThreads) {
+        for (int i = tid; i < BP * 4; i += kRhnThreads) {
           const int m = i >> 2, col = i & 3;
           float a = 0.f;
 #pragma unroll
@@ -439,33 +456,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_rhn_forward(const __grid_consta
         }
       }
       const bool need_barrier = !last || t + 1 < T;
+      GNAS_MARK(j + 1, 2);
       if (need_barrier) grid_arrive(P.bar); else __syncthreads();
       // off the critical path: stash for backward, contributions of s_j to the later nodes, bookkeeping
-      for (int it = tid; it < 4 * B; it += kThreads) {        // pre-activations of edge (j, j)
+      for (int it = tid; it < 4 * B; it += kRhnThreads) {        // pre-activations of edge (j, j)
         const int m = it % B, col = it / B;
         float c = 0.f, h = 0.f;
         for (int s = 0; s < KS; ++s) { c += part[(size_t)(s * N + col) * BP + m]; h += part[(size_t)(s * N + 4 + col) * BP + m]; }
         float* chp = P.CHT + (((size_t)t * 36 + j * (j + 1) / 2 + j) * 2) * HB + (size_t)(n0 + col) * BP + m;
         chp[0] = c; chp[HB] = h;
       }
-      for (int it = tid; it < (7 - j) * 4 * B; it += kThreads) {
+      for (int it = tid; it < (7 - j) * 4 * B; it += kRhnThreads) {
         const int m = it % B, col = (it / B) & 3, irel = 1 + it / (4 * B);
         edge_item(t, j, irel, m, col, N, KS, true);
       }
       stash_state(t, j + 1);
-      for (int i = tid; i < BP * 4; i += kThreads) accn[j * BP * 4 + i] = 0.f;
+      for (int i = tid; i < BP * 4; i += kRhnThreads) accn[j * BP * 4 + i] = 0.f;
       if (last) {
-        for (int i = tid; i < BP * 4; i += kThreads) {
+        for (int i = tid; i < BP * 4; i += kRhnThreads) {
           const int col = i / BP, m = i - col * BP;
           P.HT[(size_t)t * HB + (size_t)(n0 + col) * BP + m] = hloc[m * 4 + col];
         }
-        for (int m = tid; m < B; m += kThreads)
+        for (int m = tid; m < B; m += kRhnThreads)
           *reinterpret_cast<float4*>(P.out + ((size_t)t * B + m) * H + n0) =
               make_float4(hloc[m * 4], hloc[m * 4 + 1], hloc[m * 4 + 2], hloc[m * 4 + 3]);
       }
       bar_target += gridDim.x;
       if (need_barrier) { if (grid_wait(P.bar, P.abort_flag, bar_target, &s_abort)) return; }
       else __syncthreads();
+      GNAS_MARK(j + 1, 3);
     }
   }
   if (P.training && P.running && tid < 8) P.running[(tid >> 2) * H + n0 + (tid & 3)] = run[tid];
@@ -600,15 +619,26 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem0(const __grid_
   }
 }
 
-// out_z[n][m] += mask[n][m] * sum_k W[n][k] * D_z[k][m]   (split-K, atomics)
+// dst[c][r] = src[r][c]  (R x C -> C x R), batched over blockIdx.z
+static __global__ void __launch_bounds__(256) k_transpose(const float* src, float* dst, int R, int C) {
+  __shared__ float tile[32][33];
+  src += (size_t)blockIdx.z * R * C; dst += (size_t)blockIdx.z * R * C;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) if (r0 + i < R && c0 + tx < C) tile[i][tx] = src[(size_t)(r0 + i) * C + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) if (c0 + i < C && r0 + tx < R) dst[(size_t)(c0 + i) * R + r0 + tx] = tile[tx][i];
+}
+
+// out_z[n][m] += mask[n][m] * sum_k W[n][k] * D_z[k][m]   (split-K, atomics);  W is passed TRANSPOSED (WT[k][n])
 // CTA tile: 64 rows n x BP columns m, K range = K / ksplit, cp.async double-buffered 32-row K chunks.
 struct RhnGemm {
   int Nrows, K, BP, nz, ksplit, Hsplit;   // rows >= Hsplit go to out2/mask2 (stage 0: dx rows | dh rows)
-  const float* W; int ldw;
+  const float* WT; int ldw;               // WT[k][n], row pitch ldw (= Nrows)
   const float* D[8]; float* out[8];
   const float* mask; float* out2; const float* mask2;
 };
-constexpr int kGemmKC = 32, kGemmWP = kGemmKC + 4;
+constexpr int kGemmKC = 32;
 static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_gemm(const __grid_constant__ RhnGemm P) {
   const int z = blockIdx.z;
   const int n0 = blockIdx.x * 64;
@@ -619,8 +649,8 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_gemm(const __grid_c
   const int ncg = BP / 4;
   const int rq = tid / ncg, cg = tid - rq * ncg;
   const bool active = rq < 16;
-  __shared__ __align__(16) float Wsm[2][64 * kGemmWP];
-  __shared__ __align__(16) float Dsm[2][kGemmKC * kMaxBP];
+  GNAS_DYN_SMEM(float, gsm);                                 // nch stages of { W [32][64] | D [32][BP] }
+  const int stage_floats = kGemmKC * 64 + kGemmKC * BP;
   float acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -628,36 +658,42 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_gemm(const __grid_c
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   const float* Dz = P.D[z];
   const int nch = kper / kGemmKC;
+  const int ncols = min(64, P.Nrows - n0);           // multiple of 4 (H is a multiple of 32)
   auto issue = [&](int c) {
     const int k0 = kbeg + c * kGemmKC;
-    float* wd = Wsm[c & 1];
-    float* dd = Dsm[c & 1];
-    for (int i = tid; i < 64 * (kGemmKC / 4); i += kThreads) {       // W rows: 8 x 16-byte pieces each
-      const int r = i / (kGemmKC / 4), q = i - r * (kGemmKC / 4);
-      const int n = n0 + r < P.Nrows ? n0 + r : P.Nrows - 1;
-      cp_async16(wd + r * kGemmWP + 4 * q, P.W + (size_t)n * P.ldw + k0 + 4 * q);
+    float* wd = gsm + (size_t)c * stage_floats;
+    float* dd = wd + kGemmKC * 64;
+    for (int i = tid; i < kGemmKC * 16; i += kThreads) {
+      const int k = i >> 4, q = i & 15;
+      if (4 * q < ncols) cp_async16(wd + k * 64 + 4 * q, P.WT + (size_t)(k0 + k) * P.ldw + n0 + 4 * q);
     }
     for (int i = tid; i < kGemmKC * BP / 4; i += kThreads) cp_async16(dd + 4 * i, Dz + (size_t)k0 * BP + 4 * i);
     cp_async_commit();
   };
-  issue(0);
+  // every chunk of this CTA's K range is requested up front (<= 4 x 16 KB): one L2 round trip, not one per chunk
+  for (int c = 0; c < nch; ++c) issue(c);
   for (int c = 0; c < nch; ++c) {
-    if (c + 1 < nch) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    switch (nch - 1 - c) { case 0: cp_async_wait<0>(); break; case 1: cp_async_wait<1>(); break;
+                           case 2: cp_async_wait<2>(); break; default: cp_async_wait<3>(); break; }
     __syncthreads();
     if (active) {
-      const float* wr = Wsm[c & 1] + (4 * rq) * kGemmWP;
-      const float* dr = Dsm[c & 1] + 4 * cg;
-#pragma unroll 8
+      const float* wr = gsm + (size_t)c * stage_floats + 4 * rq;
+      const float* dr = gsm + (size_t)c * stage_floats + kGemmKC * 64 + 4 * cg;
+      float4 w = *reinterpret_cast<const float4*>(wr);
+      float4 d = *reinterpret_cast<const float4*>(dr);
+#pragma unroll
       for (int k = 0; k < kGemmKC; ++k) {
-        const float w0 = wr[k], w1 = wr[kGemmWP + k], w2 = wr[2 * kGemmWP + k], w3 = wr[3 * kGemmWP + k];
-        const float4 d = *reinterpret_cast<const float4*>(dr + k * BP);
-        acc[0][0] = fmaf(w0, d.x, acc[0][0]); acc[0][1] = fmaf(w0, d.y, acc[0][1]); acc[0][2] = fmaf(w0, d.z, acc[0][2]); acc[0][3] = fmaf(w0, d.w, acc[0][3]);
-        acc[1][0] = fmaf(w1, d.x, acc[1][0]); acc[1][1] = fmaf(w1, d.y, acc[1][1]); acc[1][2] = fmaf(w1, d.z, acc[1][2]); acc[1][3] = fmaf(w1, d.w, acc[1][3]);
-        acc[2][0] = fmaf(w2, d.x, acc[2][0]); acc[2][1] = fmaf(w2, d.y, acc[2][1]); acc[2][2] = fmaf(w2, d.z, acc[2][2]); acc[2][3] = fmaf(w2, d.w, acc[2][3]);
-        acc[3][0] = fmaf(w3, d.x, acc[3][0]); acc[3][1] = fmaf(w3, d.y, acc[3][1]); acc[3][2] = fmaf(w3, d.z, acc[3][2]); acc[3][3] = fmaf(w3, d.w, acc[3][3]);
+        const float4 x = w, y = d;
+        if (k + 1 < kGemmKC) {
+          w = *reinterpret_cast<const float4*>(wr + (k + 1) * 64);
+          d = *reinterpret_cast<const float4*>(dr + (k + 1) * BP);
+        }
+        acc[0][0] = fmaf(x.x, y.x, acc[0][0]); acc[0][1] = fmaf(x.x, y.y, acc[0][1]); acc[0][2] = fmaf(x.x, y.z, acc[0][2]); acc[0][3] = fmaf(x.x, y.w, acc[0][3]);
+        acc[1][0] = fmaf(x.y, y.x, acc[1][0]); acc[1][1] = fmaf(x.y, y.y, acc[1][1]); acc[1][2] = fmaf(x.y, y.z, acc[1][2]); acc[1][3] = fmaf(x.y, y.w, acc[1][3]);
+        acc[2][0] = fmaf(x.z, y.x, acc[2][0]); acc[2][1] = fmaf(x.z, y.y, acc[2][1]); acc[2][2] = fmaf(x.z, y.z, acc[2][2]); acc[2][3] = fmaf(x.z, y.w, acc[2][3]);
+        acc[3][0] = fmaf(x.w, y.x, acc[3][0]); acc[3][1] = fmaf(x.w, y.y, acc[3][1]); acc[3][2] = fmaf(x.w, y.z, acc[3][2]); acc[3][3] = fmaf(x.w, y.w, acc[3][3]);
       }
     }
-    __syncthreads();
   }
   if (active) {
 #pragma unroll
@@ -667,8 +703,8 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_gemm(const __grid_c
       float* o; const float* mk;
       if (n < P.Hsplit) { o = P.out[z] + (size_t)n * BP; mk = P.mask + (size_t)n * BP; }
       else { o = P.out2 + (size_t)(n - P.Hsplit) * BP; mk = P.mask2 + (size_t)(n - P.Hsplit) * BP; }
-#pragma unroll
-      for (int b = 0; b < 4; ++b) atomicAdd(&o[4 * cg + b], mk[4 * cg + b] * acc[a][b]);
+      const float4 mv = *reinterpret_cast<const float4*>(mk + 4 * cg);
+      red_add_v4(o + 4 * cg, mv.x * acc[a][0], mv.y * acc[a][1], mv.z * acc[a][2], mv.w * acc[a][3]);
     }
   }
 }
@@ -796,7 +832,7 @@ extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const floa
   pro.x = x; pro.h0 = h0; pro.xm = d->training ? x_mask : nullptr; pro.hm = d->training ? h_mask : nullptr;
   pro.xmT = ws + p.xmT; pro.xkT = ws + p.xkT; pro.hmT = ws + p.hmT; pro.h0T = ws + p.h0T; pro.ring9 = ws + p.ring + 9 * HB;
   GNAS_LAUNCH(k_rhn_prologue, dim3(ewb((long long)(d->T + 3) * HB)), dim3(256), 0, st, pro);
-  cudaMemsetAsync(ws + p.bar, 0, 64 * sizeof(float), st);
+  cudaMemsetAsync(ws + p.bar, 0, 256 * sizeof(float), st);
   RhnFwd f;
   f.T = d->T; f.B = d->B; f.BP = BP; f.H = H; f.training = d->training; f.momentum = d->bn_momentum;
   f.xmT = ws + p.xmT; f.hmT = ws + p.hmT; f.h0T = ws + p.h0T; f.W0 = W0; f.Ws = Ws; f.probs = probs;
@@ -808,7 +844,7 @@ extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const floa
                                        8 * BP * 4 + 9 * BP * 4 + 3 * BP * 4 + 36 * 5 + 8 + 8);
   const int grid = H / kNC;
 #ifdef GNAS_EMUL
-  GNAS_LAUNCH_COOP(k_rhn_forward, dim3(grid), dim3(kThreads), smem, st, f);
+  GNAS_LAUNCH_COOP(k_rhn_forward, dim3(grid), dim3(kRhnThreads), smem, st, f);
 #else
   {
     static size_t prepared = 0;
@@ -820,11 +856,11 @@ extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const floa
     int dev = 0, nsm = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rhn_forward, kThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rhn_forward, kRhnThreads, smem);
     if (per_sm * nsm < grid) { set_error("rhn_forward: grid does not fit co-resident (hidden size too large)"); return GNAS_ERR_UNSUPPORTED; }
     void* args[] = {(void*)&f};
     prof_before("k_rhn_forward", "", st);
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_rhn_forward, dim3(grid), dim3(kThreads), args, smem, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_rhn_forward, dim3(grid), dim3(kRhnThreads), args, smem, st);
     prof_after(st);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
   }
@@ -848,7 +884,9 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
   const long long HB = (long long)H * BP;
   RhnTable tb;
   rhn_table(d, tb);
-  cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)p.bwd_total, st);
+  cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)p.bwd_zero, st);
+  GNAS_LAUNCH(k_transpose, dim3((2 * H + 31) / 32, (H + 31) / 32, 8), dim3(256), 0, st, Ws, scratch + p.WsT, H, 2 * H);
+  GNAS_LAUNCH(k_transpose, dim3((2 * H + 31) / 32, (2 * H + 31) / 32, 1), dim3(256), 0, st, W0, scratch + p.W0T, 2 * H, 2 * H);
   float* dhbuf[2] = {scratch + p.dhT, scratch + p.dhT + HB};
   // dh for the last step = dout[T-1]^T
   GNAS_LAUNCH(k_rhn_dout_T, dim3((H * BP + 255) / 256), dim3(256), 0, st, dout, dhbuf[0], B, BP, H, T - 1);
@@ -858,8 +896,15 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
   bp.probs = probs; bp.dout = dout; bp.dsT = scratch + p.dsT; bp.dpacc = reinterpret_cast<double*>(scratch + p.dpacc);
   bp.tb = tb;
   const int eb = (H + 7) / 8;
-  int ksplit = 1;                       // split K = 2H so that each CTA still sees >= 2 chunks of 32
-  while (ksplit < 8 && (2 * H) % (ksplit * 2 * kGemmKC) == 0 && (2 * H) / (ksplit * 2) >= 2 * kGemmKC) ksplit *= 2;
+  int ksplit = 1;                       // split K = 2H into CTAs of at most 4 chunks of 32 (all prefetched at once)
+  while ((2 * H) / ksplit > 4 * kGemmKC && (2 * H) % (ksplit * 2 * kGemmKC) == 0) ksplit *= 2;
+  const int nch_g = (2 * H) / ksplit / kGemmKC;
+  const size_t gsm = sizeof(float) * (size_t)nch_g * (kGemmKC * 64 + kGemmKC * BP);
+#ifndef GNAS_EMUL
+  { static size_t prepared = 0;
+    if (gsm > prepared) { cudaFuncSetAttribute(k_rhn_bwd_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm); prepared = gsm; } }
+#endif
+  if (nch_g > 4 || nch_g < 1) { set_error("rhn_backward: unsupported hidden size for the GEMM split"); return GNAS_ERR_UNSUPPORTED; }
   for (int t = T - 1; t >= 0; --t) {
     float* dh_cur = dhbuf[(T - 1 - t) & 1];
     float* dh_next = dhbuf[(T - t) & 1];
@@ -870,22 +915,22 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
       GNAS_LAUNCH(k_rhn_bwd_elem, dim3(eb, i + 1), dim3(kThreads), 0, st, bp);
       RhnGemm g;
       g.Nrows = H; g.K = 2 * H; g.BP = BP; g.nz = i + 1; g.ksplit = ksplit; g.Hsplit = H;
-      g.W = Ws + (size_t)i * H * 2 * H; g.ldw = 2 * H;
+      g.WT = scratch + p.WsT + (size_t)i * H * 2 * H; g.ldw = H;
       for (int j = 0; j <= i; ++j) {
         g.D[j] = ws + p.CHT + (((size_t)t * 36 + i * (i + 1) / 2 + j) * 2) * HB;
         g.out[j] = scratch + p.dsT + (size_t)j * HB;
       }
       g.mask = ws + p.hmT; g.out2 = nullptr; g.mask2 = nullptr;
-      GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((H + 63) / 64, g.ksplit, i + 1), dim3(kThreads), 0, st, g);
+      GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((H + 63) / 64, g.ksplit, i + 1), dim3(kThreads), gsm, st, g);
     }
     GNAS_LAUNCH(k_rhn_bwd_elem0, dim3(eb), dim3(kThreads), 0, st, bp);
     RhnGemm g;
     g.Nrows = 2 * H; g.K = 2 * H; g.BP = BP; g.nz = 1; g.ksplit = ksplit; g.Hsplit = H;
-    g.W = W0; g.ldw = 2 * H;
+    g.WT = scratch + p.W0T; g.ldw = 2 * H;
     g.D[0] = ws + p.C0T + ((size_t)t * 2) * HB;
     g.out[0] = scratch + p.dxT + (size_t)t * HB; g.mask = ws + p.xkT;
     g.out2 = dh_next; g.mask2 = ws + p.hmT;
-    GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((2 * H + 63) / 64, g.ksplit, 1), dim3(kThreads), 0, st, g);
+    GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((2 * H + 63) / 64, g.ksplit, 1), dim3(kThreads), gsm, st, g);
   }
   // outputs: dx [T][B][H], dh0 [B][H], dprobs
   GNAS_LAUNCH(k_rhn_untranspose, dim3(ewb((long long)T * B * H)), dim3(256), 0, st, (const float*)(scratch + p.dxT), dx, T, B, BP, H);

@@ -105,3 +105,25 @@ def test_gradient_accumulation_semantics(backend):
     m(x, w).sum().backward()
     for n, p in m.named_parameters():
         assert relerr(p.grad, once[n]) < 1e-5, n
+
+
+def test_stem_full_width_alignment(backend):
+    """Stem at the BASELINE width (24 output channels): the weight-gradient kernel splits positions over
+    10 thread groups, which once produced rows that were not 16-byte aligned."""
+    from genome_nas_b200.model import _StemFunction
+    torch.manual_seed(0)
+    stem = torch.nn.Sequential(torch.nn.Conv1d(4, 24, 13, padding=6, bias=False), torch.nn.BatchNorm1d(24)).to(backend)
+    x = torch.zeros(3, 4, 200)
+    x.scatter_(1, torch.randint(0, 4, (3, 1, 200)), 1.0)
+    y = _StemFunction.apply(stem, x.to(backend), stem[0].weight)
+    gy = torch.randn(y.shape)
+    (y * gy.to(backend)).sum().backward()
+    ref = torch.nn.Sequential(torch.nn.Conv1d(4, 24, 13, padding=6, bias=False), torch.nn.BatchNorm1d(24)).double()
+    ref.load_state_dict({k: v.detach().cpu() for k, v in stem.state_dict().items()})
+    with torch.no_grad():
+        ref[1].running_mean.zero_(); ref[1].running_var.fill_(1.0)
+    yr = ref(x.double())
+    (yr * gy.double()).sum().backward()
+    assert relerr(y, yr) < 1e-5
+    for (n, p), (_, q) in zip(stem.named_parameters(), ref.named_parameters()):
+        assert relerr(p.grad, q.grad) < 5e-5, n

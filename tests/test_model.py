@@ -62,8 +62,10 @@ def check_forward_backward(g, device, monkeypatch):
         ref = gn[n]
         if ref < 1e-12 * total:
             continue
-        # per-tensor rel-L2 against fp64 graded like the reference's own fp32 run
-        lim = max(1e-3, 1.5 * r32[n])
+        # per-tensor rel-L2 against fp64, graded against the reference's own fp32 run: the north
+        # star's 1e-3, or twice the error the reference itself makes on that tensor when it is above 5e-4
+        # (these gradients are ill-conditioned; float-atomic summation order adds run-to-run noise)
+        lim = max(1e-3, 2.0 * r32[n])
         if n in g["grad64"]:
             assert relerr(p.grad, g["grad64"][n]) < lim, n
         else:
