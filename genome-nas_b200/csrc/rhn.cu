@@ -28,6 +28,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) { return emul_ld_acquire(p); }
 __device__ __forceinline__ int ld_volatile_i32(const int* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ float ld_cg(const float* p) { return *p; }
+__device__ __forceinline__ float4 ld_cg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ long long gnas_clock() { return 0; }
 #else
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -43,6 +44,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ int ld_volatile_i32(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ long long gnas_clock() { return clock64(); }
 #endif
 
@@ -221,16 +223,20 @@ __device__ __forceinline__ void rhn_chunk(const float* __restrict__ as, const fl
   }
 }
 
-// C[m][n] partial = sum_k A[k][m] * W[k][n]; A ([K][BP], already masked) is streamed from global/L2 through a
-// kStages-deep cp.async ring of kKCH-row chunks (one __syncthreads per chunk); the W slices are resident in
-// shared memory.  The K-split partials are left in `part`, which ALIASES the ring (safe: written after the
-// last chunk has been consumed by every thread).
-__device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const float* __restrict__ A1, int K0, int K,
-                                         int BP, int N, const float* wbase, int wstride_i, bool stage0,
-                                         float* abuf, float* part) {
+// C[m][n] partial = sum_k A[k][m] * W[k][n]; the W slices are resident in shared memory, A ([K][BP], already
+// masked) is streamed from L2 in kKCH-row chunks.  Measured on B200 (clock64 marks in the kernel): with a
+// 4-deep cp.async ring the loop ran at ~850 cycles per 8 KB chunk whatever the math -- an L2 round trip of
+// ~2500 cycles divided by 3 chunks in flight.  Shared memory is full (weights), so the in-flight window lives
+// in REGISTERS: every thread keeps its 16-byte share of the next kPre chunks (ld.global.cg, 8 x 8 KB in
+// flight per SM), and copies the oldest into a double-buffered shared tile just before it is needed.
+// One __syncthreads per chunk.  The K-split partials are left in `part`, which aliases the tiles.
+constexpr int kPre = 8;
+template <int KS>
+__device__ __forceinline__ void rhn_gemm_t(const float* __restrict__ A0, const float* __restrict__ A1, int K0, int K,
+                                           int BP, int N, const float* wbase, int wstride_i, bool stage0,
+                                           float* abuf, float* part) {
   const int tid = threadIdx.x;
   const int nrg = BP / 4, ncg = N / 4;
-  const int KS = rhn_ks(BP, N);
   const int rg = tid % nrg, cg = (tid / nrg) % ncg, ks = tid / (nrg * ncg);
   const bool active = ks < KS;
   float acc[4][4];
@@ -239,38 +245,38 @@ __device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const flo
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
   // W column group: stage 0 -> W0s[k][8]; stage j -> Wss[i][k][8] with i = cg / 2
-  const float* wcol = stage0 ? wbase + cg * 4 : wbase + (size_t)(cg >> 1) * wstride_i + (cg & 1) * 4;
+  const float* wk = (stage0 ? wbase + cg * 4 : wbase + (size_t)(cg >> 1) * wstride_i + (cg & 1) * 4) + ks * 8;
   const int nch = K / kKCH;
-  const int f4_per_chunk = kKCH * BP / 4;
-  auto issue = [&](int c) {
-    if (c < nch) {
-      float* dst = abuf + (c % kStages) * kKCH * BP;
+  const int chunk_floats = kKCH * BP;
+  const bool mine = 4 * tid < chunk_floats;          // this thread's 16-byte share of a chunk (BP = 64: everyone)
+  auto fetch = [&](int c) -> float4 {
+    if (c < nch && mine) {
       const int k0 = c * kKCH;
       const float* src = (k0 < K0) ? A0 + (size_t)k0 * BP : A1 + (size_t)(k0 - K0) * BP;
-      for (int i = tid; i < f4_per_chunk; i += kRhnThreads) cp_async16(dst + 4 * i, src + 4 * i);
+      return ld_cg4(src + 4 * tid);
     }
-    cp_async_commit();                   // always commit (possibly empty) so that group counting stays uniform
+    return make_float4(0.f, 0.f, 0.f, 0.f);
   };
+  float4 r[kPre];
 #pragma unroll
-  for (int c = 0; c < kStages - 1; ++c) issue(c);
-  for (int c = 0; c < nch; ++c) {
-    cp_async_wait<kStages - 2>();        // chunk c has landed (for this thread's copies)
-    __syncthreads();                     // ... for everyone's; and everyone is done with chunk c-1
-    issue(c + kStages - 1);              // refill the slot chunk c-1 occupied
-    if (active) {
-      const float* as = abuf + (c % kStages) * kKCH * BP + rg * 4 + ks * BP;
-      const float* wk = wcol + (size_t)(c * kKCH + ks) * 8;
-      switch (KS) {
-        case 1: rhn_chunk<1>(as, wk, BP, acc); break;
-        case 2: rhn_chunk<2>(as, wk, BP, acc); break;
-        case 4: rhn_chunk<4>(as, wk, BP, acc); break;
-        case 8: rhn_chunk<8>(as, wk, BP, acc); break;
-        default: rhn_chunk<16>(as, wk, BP, acc); break;
+  for (int u = 0; u < kPre; ++u) r[u] = fetch(u);
+  if (mine) *reinterpret_cast<float4*>(abuf + 4 * tid) = r[0];
+  __syncthreads();
+  const float* as0 = abuf + rg * 4 + ks * BP;
+  for (int c0 = 0; c0 < nch; c0 += kPre) {
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int c = c0 + u;
+      if (c < nch) {
+        // chunk c+1 (in registers since kPre-1 iterations) -> the tile chunk c-1 was read from
+        if (c + 1 < nch && mine) *reinterpret_cast<float4*>(abuf + ((c + 1) & 1) * chunk_floats + 4 * tid) = r[(u + 1) % kPre];
+        r[u] = fetch(c + kPre);
+        if (active) rhn_chunk<KS>(as0 + (c & 1) * chunk_floats, wk, BP, acc);
+        wk += kKCH * 8;
+        __syncthreads();
       }
     }
   }
-  cp_async_wait<0>();
-  __syncthreads();                       // ring no longer read: `part` may overwrite it
   // partials are stored column-major ([ks][n][BP], 4 consecutive batch rows per 128-bit store): conflict-free
   // for these stores and for the batch-row-fastest reads of the elementwise phase
   if (active) {
@@ -281,6 +287,18 @@ __device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const flo
   __syncthreads();
 }
 
+__device__ __forceinline__ void rhn_gemm(const float* __restrict__ A0, const float* __restrict__ A1, int K0, int K,
+                                         int BP, int N, const float* wbase, int wstride_i, bool stage0,
+                                         float* abuf, float* part) {
+  switch (rhn_ks(BP, N)) {
+    case 1: rhn_gemm_t<1>(A0, A1, K0, K, BP, N, wbase, wstride_i, stage0, abuf, part); break;
+    case 2: rhn_gemm_t<2>(A0, A1, K0, K, BP, N, wbase, wstride_i, stage0, abuf, part); break;
+    case 4: rhn_gemm_t<4>(A0, A1, K0, K, BP, N, wbase, wstride_i, stage0, abuf, part); break;
+    case 8: rhn_gemm_t<8>(A0, A1, K0, K, BP, N, wbase, wstride_i, stage0, abuf, part); break;
+    default: rhn_gemm_t<16>(A0, A1, K0, K, BP, N, wbase, wstride_i, stage0, abuf, part); break;
+  }
+}
+
 __global__ void __launch_bounds__(kRhnThreads, 1) k_rhn_forward(const __grid_constant__ RhnFwd P) {
   const int H = P.H, B = P.B, BP = P.BP, T = P.T;
   const int n0 = blockIdx.x * kNC;
@@ -289,8 +307,8 @@ __global__ void __launch_bounds__(kRhnThreads, 1) k_rhn_forward(const __grid_con
   GNAS_DYN_SMEM(float, smem);
   float* W0s = smem;                          // [2H][8]
   float* Wss = W0s + (size_t)2 * H * 8;       // [8][H][8]
-  float* abuf = Wss + (size_t)8 * H * 8;      // [kStages][kKCH][BP]  streamed operand ring
-  float* part = abuf;                         // [KS][BP][N] (<= BP*64 floats) aliases the ring
+  float* abuf = Wss + (size_t)8 * H * 8;      // [2][kKCH][BP] operand tiles; the region is 128*BP floats because
+  float* part = abuf;                         // ... the K-split partials [KS][N][BP] (<= 128*BP floats) alias it
   float* accn = abuf + kStages * kKCH * BP;   // [8][BP][4]  pending node accumulators
   float* sloc = accn + 8 * BP * 4;            // [9][BP][4]  own columns of s_0..s_8
   float* hloc = sloc + 9 * BP * 4;            // [BP][4]     own columns of h_{t-1}
