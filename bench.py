@@ -167,8 +167,17 @@ def family_of(name):
     return name.split(" ")[0]
 
 
+def dbg(msg):
+    if os.environ.get("GNAS_BENCH_DEBUG"):
+        sys.stderr.write(f"[bench r{os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}\n")
+        sys.stderr.flush()
+
+
 def main():
     args = parse()
+    if os.environ.get("GNAS_BENCH_DEBUG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["GNAS_BENCH_DEBUG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -199,9 +208,12 @@ def main():
     sn, sr, sw = switches()
     model = G.RNNModelSearch(SEQ, 0.05, 0.1, 8, NCLS, 6, 4, 4, 3, True, 0.2, None, 'TF_bindings', sn, sr, sw, 0.0, *a)
     model.to(dev).train()
+    dbg("model built")
     stepper = G.SearchStep(model, process_group=None, world_size=world)
     if world > 1:
         dist.broadcast(stepper.region.flat, 0)
+        torch.cuda.synchronize()
+    dbg("parameters broadcast")
     torch.manual_seed(1000 + rank)       # per-rank dropout masks
     host = [t.pin_memory() for pair in (O.synthetic_batch(B, SEQ, NCLS, 2 * rank), O.synthetic_batch(B, SEQ, NCLS, 2 * rank + 1))
             for t in pair]
@@ -241,6 +253,9 @@ def main():
         loss_host.copy_(torch.stack([la, lw]), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    step_resident()
+    torch.cuda.synchronize()
+    dbg("first eager step done")
     mode = "eager"
     if not args.no_graph:
         try:
@@ -248,12 +263,16 @@ def main():
             mode = "cuda-graph"
         except Exception as e:     # noqa: BLE001 -- report and keep measuring in eager mode
             sys.stderr.write(f"[bench] CUDA-graph capture unavailable ({type(e).__name__}: {e}); eager launches\n")
+    dbg(f"launch mode {mode}")
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    torch.cuda.synchronize()
+    dbg("warm-up done")
     clocks = Clocks(local)
     clocks.start()
     l0 = _lib.kernel_launches()
     ms = timed(step_resident, args.steps)
+    dbg("timed region done")
     launches = _lib.kernel_launches() - l0
     if stepper.graph is not None:      # replays do not pass through the host-side launch counter
         launches = stepper.graph_launches * args.steps
@@ -270,6 +289,7 @@ def main():
     if rank == 0:
         _lib.profile(True)
         nprof = 2
+        stepper.world = 1            # rank-0-only pass: no collectives (the other ranks are already done)
         for _ in range(nprof):
             stepper._draw_static_masks() if stepper.graph is not None else None
             stepper._step_eager(xt, yt, xv, yv)
