@@ -313,13 +313,16 @@ def main():
                  "rhn_fwd": 2 * 42 * (2 * B * 1024 * 1024 + 36 * 2 * B * 512 * 1024),
                  "rhn_bwd_gemm": 2 * 42 * (2 * B * 1024 * 1024 + 36 * 2 * B * 512 * 1024),
                  "rhn_wgrad": 42 * (2 * B * 1024 * 1024 + 36 * 2 * B * 512 * 1024)}
+        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu captures under
+        # profiles/ (r01_ncu_rhn_layer_T42_B64_H512.csv, r01_ncu_cell5_C128_L125to42.csv); None = not captured
+        ncu_traffic = {"rhn_fwd": 2.826e7 + 4.126e8, "rhn_bwd_gemm": 4.121e6 + 5.1, "rhn_wgrad": 2.75e8 + 4.04e7}
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "measured (MEASURED_PEAKS.json bf16 sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
         if top in flops:
             launches_top, t_top = fam[top]
             ach = flops[top] / (t_top / 1e3) / 1e12
             roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": ach / peak_tf, "traffic": None, "peak_source": peak_src,
+                        "frac": ach / peak_tf, "traffic": ncu_traffic.get(top), "peak_source": peak_src,
                         "launches_per_step": launches_top, "ms_per_step": t_top,
                         "note": "fp32 CUDA-core kernel (parity needs fp32-class accuracy): also "
                                 f"{ach / 72.0:.3f} of the ~72 TFLOP/s nominal fp32 pipe"}

@@ -150,22 +150,36 @@ __global__ void __launch_bounds__(kThreads) k_dense_bwd_dx(const __grid_constant
   const int lbase = m0 / S + P.pad / S - (NT - 1);
   const int Wu = 4 * nq + NT + 1;
   const int Wp = (Wu + 3) / 4 * 4 + 4;
+  // Same two-stage pipeline as the forward kernel: weights of the next chunk of KC output channels by
+  // cp.async, (g, z) rows of the next chunk prefetched into registers, dz = A*g + Bz*z + D formed on store.
+  constexpr int NPRE = 6;
   GNAS_DYN_SMEM(float, smem);
-  float* ds = smem;                               // [KC][Wp]  dz tile
-  float* ws = ds + KC * Wp;                       // [KC][KW][Cin]
-  float* ssum = ws + KC * KW * Cin;               // [2][Cin]
+  const int ds_sz = KC * Wp, ws_sz = KC * KW * Cin;
+  float* dsb = smem;                              // [2][KC][Wp]  dz tiles
+  float* wsb = dsb + 2 * ds_sz;                   // [2][KC][KW][Cin]
+  float* ssum = wsb + 2 * ws_sz;                  // [2][Cin]
   for (int i = tid; i < 2 * Cin; i += kThreads) ssum[i] = 0.f;
   float acc[TM][4];
 #pragma unroll
   for (int m = 0; m < TM; ++m)
 #pragma unroll
     for (int n = 0; n < 4; ++n) acc[m][n] = 0.f;
-  for (int c0 = 0; c0 < J.Cout; c0 += KC) {
+  const int nchunks = J.Cout / KC;
+  const bool prefetch = KC <= kThreads / 32 && Wp <= 32 * NPRE;
+  auto load_w = [&](int c, int buf) {
+    const float* src = J.wt + (long long)c * ws_sz;
+    float* dst = wsb + buf * ws_sz;
+    for (int i = 4 * tid; i < ws_sz; i += 4 * kThreads) gnas_cp_async16(dst + i, src + i);
+    gnas_cp_async_commit();
+  };
+  auto load_d_sync = [&](int c, int buf) {
+    float* ds = dsb + buf * ds_sz;
     for (int co = warp; co < KC; co += kThreads / 32) {
-      const float* gr = J.g + (long long)b * J.gbs + (long long)(c0 + co) * J.Lo;
-      const float* zr = J.z ? J.z + (long long)b * J.zbs + (long long)(c0 + co) * J.Lo : nullptr;
+      const int ch = c * KC + co;
+      const float* gr = J.g + (long long)b * J.gbs + (long long)ch * J.Lo;
+      const float* zr = J.z ? J.z + (long long)b * J.zbs + (long long)ch * J.Lo : nullptr;
       float A = 1.f, Bz = 0.f, D = 0.f;
-      if (zr) { A = J.coef[c0 + co]; Bz = J.coef[J.Cout + c0 + co]; D = J.coef[2 * J.Cout + c0 + co]; }
+      if (zr) { A = J.coef[ch]; Bz = J.coef[J.Cout + ch]; D = J.coef[2 * J.Cout + ch]; }
       _Pragma("unroll 4")
       for (int p = lane; p < Wp; p += 32) {
         const int l = lbase + p;
@@ -174,14 +188,46 @@ __global__ void __launch_bounds__(kThreads) k_dense_bwd_dx(const __grid_constant
         ds[co * Wp + p] = v;
       }
     }
-    {
-      const float4* src = reinterpret_cast<const float4*>(J.wt + (long long)c0 * KW * Cin);
-      float4* dst = reinterpret_cast<float4*>(ws);
-      const int n4 = KC * KW * Cin / 4;
-      for (int i = tid; i < n4; i += kThreads) dst[i] = src[i];
+  };
+  float gpre[NPRE], zpre[NPRE];
+  auto fetch_d = [&](int c) {
+    if (warp < KC) {
+      const int ch = c * KC + warp;
+      const float* gr = J.g + (long long)b * J.gbs + (long long)ch * J.Lo;
+      const float* zr = J.z ? J.z + (long long)b * J.zbs + (long long)ch * J.Lo : nullptr;
+#pragma unroll
+      for (int q = 0; q < NPRE; ++q) {
+        const int p = lane + 32 * q, l = lbase + p;
+        const bool in = p < Wu && l >= 0 && l < J.Lo;
+        gpre[q] = in ? gr[l] : 0.f;
+        zpre[q] = (in && zr) ? zr[l] : 0.f;
+      }
     }
-    __syncthreads();
+  };
+  auto store_d = [&](int c, int buf) {
+    if (warp < KC) {
+      const int ch = c * KC + warp;
+      float* ds = dsb + buf * ds_sz + warp * Wp;
+      float A = 1.f, Bz = 0.f, D = 0.f;
+      if (J.z) { A = J.coef[ch]; Bz = J.coef[J.Cout + ch]; D = J.coef[2 * J.Cout + ch]; }
+#pragma unroll
+      for (int q = 0; q < NPRE; ++q) {
+        const int p = lane + 32 * q, l = lbase + p;
+        if (p < Wp) ds[p] = (p < Wu && l >= 0 && l < J.Lo) ? fmaf(A, gpre[q], fmaf(Bz, zpre[q], D)) : 0.f;
+      }
+    }
+  };
+  load_w(0, 0);
+  load_d_sync(0, 0);
+  gnas_cp_async_wait_all();
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1, nxt = cur ^ 1;
+    const bool more = c + 1 < nchunks;
+    if (more) { load_w(c + 1, nxt); if (prefetch) fetch_d(c + 1); }
     if (active && nt > 0) {
+      const float* ds = dsb + cur * ds_sz;
+      const float* ws = wsb + cur * ws_sz;
       for (int co = 0; co < KC; ++co) {
         float xr[NX4 * 4];
         if (S == 1) {
@@ -206,6 +252,10 @@ __global__ void __launch_bounds__(kThreads) k_dense_bwd_dx(const __grid_constant
           }
         }
       }
+    }
+    if (more) {
+      if (prefetch) store_d(c + 1, nxt); else load_d_sync(c + 1, nxt);
+      gnas_cp_async_wait_all();
     }
     __syncthreads();
   }

@@ -61,10 +61,15 @@ __global__ void __launch_bounds__(kThreads) k_dense_fwd(const __grid_constant__ 
   constexpr int NX4 = (NX + 3) / 4;
   const int Wu = (TL - 1) * S + KW;             // used width of an xs row
   const int Wp = (Wu + 3) / 4 * 4 + 4;          // padded pitch (window over-read stays inside)
+  // Two-stage software pipeline over chunks of KC input channels: the weights of chunk c+1 arrive by
+  // cp.async and the raw input rows of chunk c+1 are fetched into registers while chunk c is multiplied;
+  // the input transform (ReLU / BN+ReLU) is applied when the registers are stored to shared memory.
+  constexpr int NPRE = 10;                      // input elements a lane may hold in flight per row
   GNAS_DYN_SMEM(float, smem);
-  float* xs = smem;                             // [KC][Wp]
-  float* ws = xs + KC * Wp;                     // [KC][KW][Cout]
-  float* ssum = ws + KC * KW * Cout;            // [2][Cout]
+  const int xs_sz = KC * Wp, ws_sz = KC * KW * Cout;
+  float* xsb = smem;                            // [2][KC][Wp]
+  float* wsb = xsb + 2 * xs_sz;                 // [2][KC][KW][Cout]
+  float* ssum = wsb + 2 * ws_sz;                // [2][Cout]
   for (int i = tid; i < 2 * Cout; i += kThreads) ssum[i] = 0.f;
   float acc[TM][4];
 #pragma unroll
@@ -73,11 +78,20 @@ __global__ void __launch_bounds__(kThreads) k_dense_fwd(const __grid_constant__ 
     for (int n = 0; n < 4; ++n) acc[m][n] = 0.f;
   const int in0 = l0 * S - P.pad;
   const float* xb = J.x + (long long)b * J.xbs;
-  for (int c0 = 0; c0 < J.Cin; c0 += KC) {
+  const int nchunks = J.Cin / KC;
+  const bool prefetch = KC <= kThreads / 32 && Wp <= 32 * NPRE;     // one row per warp, <= NPRE elements per lane
+  auto load_w = [&](int c, int buf) {
+    const float* src = J.wp + (long long)c * ws_sz;
+    float* dst = wsb + buf * ws_sz;
+    for (int i = 4 * tid; i < ws_sz; i += 4 * kThreads) gnas_cp_async16(dst + i, src + i);
+    gnas_cp_async_commit();
+  };
+  auto load_x_sync = [&](int c, int buf) {
+    float* xs = xsb + buf * xs_sz;
     for (int ci = warp; ci < KC; ci += kThreads / 32) {
-      const float* xr = xb + (long long)(c0 + ci) * J.Lin;
+      const float* xr = xb + (long long)(c * KC + ci) * J.Lin;
       float mean = 0.f, rstd = 1.f;
-      if (J.tin >= T_BN_RELU) { mean = J.in_stat[c0 + ci]; rstd = J.in_stat[J.Cin + c0 + ci]; }
+      if (J.tin >= T_BN_RELU) { mean = J.in_stat[c * KC + ci]; rstd = J.in_stat[J.Cin + c * KC + ci]; }
       _Pragma("unroll 4")
       for (int p = lane; p < Wp; p += 32) {
         const int pos = in0 + p;
@@ -86,14 +100,41 @@ __global__ void __launch_bounds__(kThreads) k_dense_fwd(const __grid_constant__ 
         xs[ci * Wp + p] = v;
       }
     }
-    {
-      const float4* src = reinterpret_cast<const float4*>(J.wp + (long long)c0 * KW * Cout);
-      float4* dst = reinterpret_cast<float4*>(ws);
-      const int n4 = KC * KW * Cout / 4;
-      for (int i = tid; i < n4; i += kThreads) dst[i] = src[i];
+  };
+  float xpre[NPRE];
+  auto fetch_x = [&](int c) {
+    if (warp < KC) {
+      const float* xr = xb + (long long)(c * KC + warp) * J.Lin;
+#pragma unroll
+      for (int q = 0; q < NPRE; ++q) {
+        const int p = lane + 32 * q, pos = in0 + p;
+        xpre[q] = (p < Wu && pos >= 0 && pos < J.Lin) ? xr[pos] : 0.f;
+      }
     }
-    __syncthreads();
+  };
+  auto store_x = [&](int c, int buf) {
+    if (warp < KC) {
+      float* xs = xsb + buf * xs_sz + warp * Wp;
+      float mean = 0.f, rstd = 1.f;
+      if (J.tin >= T_BN_RELU) { mean = J.in_stat[c * KC + warp]; rstd = J.in_stat[J.Cin + c * KC + warp]; }
+#pragma unroll
+      for (int q = 0; q < NPRE; ++q) {
+        const int p = lane + 32 * q, pos = in0 + p;
+        if (p < Wp) xs[p] = (p < Wu && pos >= 0 && pos < J.Lin) ? apply_tin(xpre[q], J.tin, mean, rstd) : 0.f;
+      }
+    }
+  };
+  load_w(0, 0);
+  load_x_sync(0, 0);
+  gnas_cp_async_wait_all();
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int cur = c & 1, nxt = cur ^ 1;
+    const bool more = c + 1 < nchunks;
+    if (more) { load_w(c + 1, nxt); if (prefetch) fetch_x(c + 1); }
     if (active) {
+      const float* xs = xsb + cur * xs_sz;
+      const float* ws = wsb + cur * ws_sz;
       for (int ci = 0; ci < KC; ++ci) {
         float xr[NX4 * 4];
         const float4* xp = reinterpret_cast<const float4*>(xs + ci * Wp + lg * 4 * S);
@@ -110,6 +151,10 @@ __global__ void __launch_bounds__(kThreads) k_dense_fwd(const __grid_constant__ 
             for (int n = 0; n < 4; ++n) acc[m][n] = fmaf(w[m], xr[n * S + t], acc[m][n]);
         }
       }
+    }
+    if (more) {
+      if (prefetch) store_x(c + 1, nxt); else load_x_sync(c + 1, nxt);
+      gnas_cp_async_wait_all();
     }
     __syncthreads();
   }

@@ -78,6 +78,20 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 #endif
 }
 
+// 16-byte asynchronous global -> shared copy (L2 only) and its group fences
+#ifdef GNAS_EMUL
+__device__ __forceinline__ void gnas_cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+__device__ __forceinline__ void gnas_cp_async_commit() {}
+__device__ __forceinline__ void gnas_cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void gnas_cp_async16(void* dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void gnas_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void gnas_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

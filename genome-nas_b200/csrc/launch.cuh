@@ -33,7 +33,7 @@ static inline int choose_kc(int kw, const int* cins, int n, int cout, int wp) {
   for (int i = 1; i < n; ++i) g = gcd_int(g, cins[i]);
   if (kw != 1) { int kc = cout > 64 ? 4 : 8; while (g % kc) kc >>= 1; return kc; }   // <= 32 KB of weights per chunk
   int kc = g;
-  while (kc > 8 && kc % 2 == 0 && sizeof(float) * ((size_t)kc * wp + (size_t)kc * cout) > 96 * 1024) kc /= 2;
+  while (kc > 8 && kc % 2 == 0 && sizeof(float) * ((size_t)kc * wp + (size_t)kc * cout) > 48 * 1024) kc /= 2;
   return kc;
 }
 
@@ -47,7 +47,7 @@ static void launch_dense_fwd_t(DenseBatch& b, int maxLout, cudaStream_t st) {
   int cins[kMaxDense];
   for (int i = 0; i < b.n; ++i) cins[i] = b.j[i].Cin;
   b.KC = choose_kc(KW, cins, b.n, b.Cout, Wp);
-  const size_t smem = sizeof(float) * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cout + 2 * b.Cout);
+  const size_t smem = sizeof(float) * (2 * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cout) + 2 * b.Cout);
   GNAS_PREP_SMEM((k_dense_fwd<KW, S, TM>), smem);
   dim3 grid(cdiv(maxLout, b.TL), b.B, b.n);
   GNAS_LAUNCH((k_dense_fwd<KW, S, TM>), grid, dim3(kThreads), smem, st, b);
@@ -120,7 +120,7 @@ static void launch_dense_dx_t(DxBatch& b, int maxLin, cudaStream_t st) {
   int couts[kMaxDense];
   for (int i = 0; i < b.n; ++i) couts[i] = b.j[i].Cout;
   b.KC = choose_kc(KW, couts, b.n, b.Cin, Wp);
-  const size_t smem = sizeof(float) * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cin + 2 * b.Cin);
+  const size_t smem = sizeof(float) * (2 * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cin) + 2 * b.Cin);
   GNAS_PREP_SMEM((k_dense_bwd_dx<KW, S, TM>), smem);
   dim3 grid(cdiv(maxLin, 4 * S * b.nq), b.B, b.n);
   GNAS_LAUNCH((k_dense_bwd_dx<KW, S, TM>), grid, dim3(kThreads), smem, st, b);
