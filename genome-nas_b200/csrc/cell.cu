@@ -2,6 +2,11 @@
 // Replaces darts_tools/model_discCNN.py:46-201 (MixedOp, CNN_Cell_search) and the
 // operator zoo generalNAS_tools/operations_14_9.py behind include/gnas.h.
 #include "launch.cuh"
+#ifndef GNAS_TC_DEFAULT
+#define GNAS_TC_DEFAULT 1
+#endif
+#include "conv15_tc.cuh"
+#include <cstdlib>
 #include "../../include/gnas.h"
 
 namespace gnas {
@@ -49,6 +54,69 @@ struct CellPlan {
 };
 
 inline long long al4(long long x) { return (x + 3) / 4 * 4; }
+
+// tcgen05 path for the stride-1 conv_15 convolutions (conv15_tc.cuh); GNAS_TC=0 selects the SIMT kernels
+inline bool tc_enabled() {
+#ifdef GNAS_EMUL
+  return false;
+#else
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GNAS_TC"); v = s ? atoi(s) : GNAS_TC_DEFAULT; }
+  return v != 0;
+#endif
+}
+inline bool tc_on(int C, int stride) {
+#ifdef GNAS_EMUL
+  (void)C; (void)stride; return false;
+#else
+  return tc_enabled() && stride == 1 && tc::tc_supported(C);
+#endif
+}
+// debugging aid: GNAS_TC_PART bit 0 = forward, bit 1 = data gradient of the second conv, bit 2 = of the first conv
+inline bool tc_part(int bit) {
+  static int v = -1;
+  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 7; }
+  return (v >> bit) & 1;
+}
+#ifndef GNAS_EMUL
+// the same jobs, handed to the tensor-core kernel
+int launch_conv15_fwd_tc(DenseBatch& db, cudaStream_t st) {
+  tc::TcBatch tb; tb.n = 0; tb.B = db.B; tb.C = db.Cout;
+  for (int i = 0; i < db.n; ++i) {
+    const DenseJob& j = db.j[i];
+    tc::TcJob& t = tb.j[tb.n++];
+    t.x = j.x; t.xbs = j.xbs; t.x2 = nullptr; t.x2bs = 0; t.in_stat = j.in_stat; t.w = j.wp;
+    t.z = j.z; t.zbs = j.zbs; t.acc = j.acc; t.mref = nullptr; t.mrbs = 0; t.mstat = nullptr;
+    t.L = j.Lout; t.tin = j.tin; t.omode = O_STORE;
+  }
+  db.n = 0;
+  return tc::launch_conv15_tc(tb, st);
+}
+int launch_conv15_dx_tc(DxBatch& xb, cudaStream_t st) {
+  tc::TcBatch tb; tb.n = 0; tb.B = xb.B; tb.C = xb.Cin;
+  for (int i = 0; i < xb.n; ++i) {
+    const DxJob& j = xb.j[i];
+    tc::TcJob& t = tb.j[tb.n++];
+    t.x = j.g; t.xbs = j.gbs; t.x2 = j.z; t.x2bs = j.zbs; t.in_stat = j.coef; t.w = j.wt;
+    t.z = j.out; t.zbs = j.obs; t.acc = j.omode == O_BNRELU_STORE ? j.bacc : nullptr;
+    t.mref = j.xin; t.mrbs = j.xibs; t.mstat = j.xin_stat;
+    t.L = j.Lo; t.tin = -1; t.omode = j.omode;
+  }
+  xb.n = 0;
+  return tc::launch_conv15_tc(tb, st);
+}
+void pack_tc(tc::TcPackBatch& pb, cudaStream_t st) {
+  if (pb.n == 0) return;
+  GNAS_LAUNCH(tc::k_pack_tc, dim3(8, pb.n), dim3(256), 0, st, pb);
+  pb.n = 0;
+}
+#else
+int launch_conv15_fwd_tc(DenseBatch&, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
+int launch_conv15_dx_tc(DxBatch&, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
+#endif
+inline bool tc_fwd_on(int C, int stride) { return tc_on(C, stride) && tc_part(0); }
+inline bool tc_dx_on(int C, int stride, int conv) { return tc_on(C, stride) && tc_part(conv == 1 ? 1 : 2); }
+inline long long conv15_pack_floats(int C) { return (long long)C * C * 15 * (tc_on(C, 1) ? 2 : 1); }
 
 int validate(const GnasCellDesc* d) {
   if (!d) { set_error("null descriptor"); return GNAS_ERR_ARG; }
@@ -124,7 +192,7 @@ void make_plan(const GnasCellDesc* d, CellPlan& P) {
         case GNAS_SKIP: if (E.stride > 1) { nt = 1; npk[0] = C * C; } break;
         case GNAS_SEP15: case GNAS_SEP9: nt = 4; npk[0] = npk[1] = C * C; break;
         case GNAS_DIL15: case GNAS_DIL9: nt = 2; npk[0] = C * C; break;
-        case GNAS_CONV15: nt = 2; npk[0] = npk[1] = C * C * 15; break;
+        case GNAS_CONV15: nt = 2; npk[0] = npk[1] = (int)conv15_pack_floats(C); break;
         default: break;
       }
       for (int i = 0; i < nt; ++i) { O.t[i] = o; o += al4(P.nCL_out); }
@@ -146,7 +214,7 @@ void make_plan(const GnasCellDesc* d, CellPlan& P) {
     for (int i = 0; i < 9; ++i) { P.tmp[s][i] = o; o += al4(P.nCL_out); }
   for (int e = 0; e < d->n_edges; ++e) {
     OpPlan& O = P.e[e].op[GNAS_CONV15];
-    if (O.on) for (int i = 0; i < 2; ++i) { O.pkb[i] = o; o += al4((long long)C * C * 15); }
+    if (O.on) for (int i = 0; i < 2; ++i) { O.pkb[i] = o; o += al4(conv15_pack_floats(C)); }
   }
   P.bwd_total = o;
 }
@@ -284,7 +352,7 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     j.Cin = C; j.Lin = Lin; j.Lout = Lo; j.tin = T_RELU;
     fin_add(e, GNAS_CONV15, 0);
   }
-  c.rc |= launch_dense_fwd(15, S, db, c.st);
+  c.rc |= tc_fwd_on(C, S) ? launch_conv15_fwd_tc(db, c.st) : launch_dense_fwd(15, S, db, c.st);
   finalize(c, fs, fc, fr, nf);
   nf = 0;
   // ---- stage 2 (sep_conv second half, conv_15 second conv) reads BN+ReLU of stage 1 on the fly
@@ -326,7 +394,7 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     j.Cin = C; j.Lin = Lo; j.Lout = Lo; j.tin = T_BN_RELU;
     fin_add(e, GNAS_CONV15, 1);
   }
-  c.rc |= launch_dense_fwd(15, 1, db, c.st);
+  c.rc |= tc_fwd_on(C, 1) ? launch_conv15_fwd_tc(db, c.st) : launch_dense_fwd(15, 1, db, c.st);
   finalize(c, fs, fc, fr, nf);
 }
 
@@ -367,6 +435,9 @@ void pack_forward(Ctx& c) {
   const GnasCellDesc* d = c.d;
   const int C = d->C;
   PackBatch pb; pb.n = 0;
+#ifndef GNAS_EMUL
+  tc::TcPackBatch tp; tp.n = 0;
+#endif
   auto add = [&](const float* src, float* dst, int co, int ci, int kw, int mode) {
     PackJob& j = pb.j[pb.n++];
     j.src = src; j.dst = dst; j.Cout = co; j.Cin = ci; j.KW = kw; j.mode = mode;
@@ -384,9 +455,22 @@ void pack_forward(Ctx& c) {
       if (k == GNAS_SKIP && E.stride > 1) add(c.W(e, k, 0), c.ws + O.pk[0], C, C, 1, 0);
       if (k == GNAS_SEP15 || k == GNAS_SEP9) { add(c.W(e, k, 1), c.ws + O.pk[0], C, C, 1, 0); add(c.W(e, k, 3), c.ws + O.pk[1], C, C, 1, 0); }
       if (k == GNAS_DIL15 || k == GNAS_DIL9) add(c.W(e, k, 1), c.ws + O.pk[0], C, C, 1, 0);
-      if (k == GNAS_CONV15) { add(c.W(e, k, 0), c.ws + O.pk[0], C, C, 15, 0); add(c.W(e, k, 1), c.ws + O.pk[1], C, C, 15, 0); }
+      if (k == GNAS_CONV15) {
+        for (int i = 0; i < 2; ++i) {
+          const int cs = i == 0 ? E.stride : 1;
+          if (!tc_fwd_on(C, cs)) { add(c.W(e, k, i), c.ws + O.pk[i], C, C, 15, 0); continue; }
+#ifndef GNAS_EMUL
+          tc::TcPackJob& t = tp.j[tp.n++];
+          t.src = c.W(e, k, i); t.dst = c.ws + O.pk[i]; t.C = C; t.mode = 0;
+          if (tp.n == 64) pack_tc(tp, c.st);
+#endif
+        }
+      }
     }
   }
+#ifndef GNAS_EMUL
+  pack_tc(tp, c.st);
+#endif
   if (pb.n) GNAS_LAUNCH(k_pack_weights, dim3(8, pb.n), dim3(256), 0, c.st, pb);
 }
 
@@ -592,7 +676,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         w.Cin = C; w.Lo = Lo; w.Lin = Lo; w.tin = T_BN_RELU;
       }
     }
-    c.rc |= launch_dense_dx(15, 1, xb, c.st);
+    c.rc |= tc_dx_on(C, 1, 1) ? launch_conv15_dx_tc(xb, c.st) : launch_dense_dx(15, 1, xb, c.st);
     c.rc |= launch_conv_wgrad(15, 1, 7, gb, c.st);
     // -- inner BN coefficients (w = 1)
     {
@@ -657,7 +741,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         w.Cin = C; w.Lo = Lo; w.Lin = Lin; w.tin = T_RELU;
       }
     }
-    c.rc |= launch_dense_dx(15, S, xb, c.st);
+    c.rc |= tc_dx_on(C, S, 0) ? launch_conv15_dx_tc(xb, c.st) : launch_dense_dx(15, S, xb, c.st);
     c.rc |= launch_conv_wgrad(15, S, 7, gb, c.st);
   }
 }
@@ -709,14 +793,29 @@ void preprocess_backward(Ctx& c, float* ds0, float* ds1, int need_wgrad) {
 void pack_backward(Ctx& c) {
   const int C = c.d->C;
   PackBatch pb; pb.n = 0;
+#ifndef GNAS_EMUL
+  tc::TcPackBatch tp; tp.n = 0;
+#endif
   for (int e = 0; e < c.P.n_edges; ++e) {
     const OpPlan& O = c.P.e[e].op[GNAS_CONV15];
     if (!O.on) continue;
     for (int i = 0; i < 2; ++i) {
+      const int cs = i == 0 ? c.P.e[e].stride : 1;
+      if (tc_dx_on(C, cs, i)) {
+#ifndef GNAS_EMUL
+        tc::TcPackJob& t = tp.j[tp.n++];
+        t.src = c.W(e, GNAS_CONV15, i); t.dst = c.scratch + O.pkb[i]; t.C = C; t.mode = 1;
+        if (tp.n == 64) pack_tc(tp, c.st);
+#endif
+        continue;
+      }
       PackJob& j = pb.j[pb.n++];
       j.src = c.W(e, GNAS_CONV15, i); j.dst = c.scratch + O.pkb[i]; j.Cout = C; j.Cin = C; j.KW = 15; j.mode = 1;
     }
   }
+#ifndef GNAS_EMUL
+  pack_tc(tp, c.st);
+#endif
   if (pb.n) GNAS_LAUNCH(k_pack_weights, dim3(8, pb.n), dim3(256), 0, c.st, pb);
 }
 

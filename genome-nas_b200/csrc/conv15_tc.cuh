@@ -1,0 +1,448 @@
+// conv_15 (dense 15-tap Conv1d, stride 1, C -> C) on the 5th-generation tensor cores:
+// implicit GEMM  D[128 positions][C_out] += A_tap[128][8 ch] * B_tap[C_out][8 ch]^T  issued as
+// tcgen05.mma kind::tf32 with the accumulator in TMEM, error-compensated 3xTF32
+// (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate) because plain TF32 destroys the gradients
+// (SURVEY.md App. C).  Replaces the arithmetic of generalNAS_tools/operations_14_9.py:67-81 for the
+// stride-1 convolutions of conv_15 (forward and, with transposed / tap-flipped weights, the data gradient).
+//
+// Shared-memory layouts are the no-swizzle K-major canonical form ((8,m),(4,2)):((16B,SBO),(4B,LBO)):
+//   A (activations): [4-channel group][row][4 floats]; a row is a sequence position, so the tap shift of the
+//                    implicit GEMM is a +16-byte offset of the descriptor start address (no im2col copy).
+//   B (weights)    : [tap][4-channel group][C_out row][4 floats], pre-split into hi/lo by k_pack_tc.
+#pragma once
+#include "common.cuh"
+#include "cnn_fwd.cuh"
+
+#ifndef GNAS_EMUL
+namespace gnas {
+namespace tc {
+
+constexpr int kRowsA = 144;          // 128 output rows + 14 halo rows (+2 pad): rows of one 4-channel group
+constexpr int kTcThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return u; }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), SWIZZLE_NONE
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ uint32_t make_idesc(int N) {
+  // cute::UMMA::InstrDescriptor: c_format F32 (1) [4,6), a/b format TF32 (2) [7,10)/[10,13), K-major A and B,
+  // n_dim = N>>3 [17,23), m_dim = 128>>4 [24,29)
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// bounded wait: a kernel that would otherwise hang traps instead (the GPU must never be left spinning)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 2000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------ weight packing (hi | lo, tensor-core layout)
+// dst[half][g][tap][kc][n][e]  (g: group of 8 reduction channels, kc: 4-channel core matrix, n: output row, e: 0..3)
+// mode 0 (forward): n = co, reduction channel = ci, tap as is;   mode 1 (data gradient): n = ci, reduction = co,
+// tap flipped (out[m] = sum_t W[.,.,t] dz[m + 7 - t]  ==  conv with taps t' = 14 - t).
+struct TcPackJob { const float* src; float* dst; int C, mode; };
+struct TcPackBatch { int n; TcPackJob j[64]; };
+static __global__ void __launch_bounds__(256) k_pack_tc(const __grid_constant__ TcPackBatch P) {
+  const TcPackJob& J = P.j[blockIdx.y];
+  const int C = J.C, total = C * C * 15;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i % 15, ci = (i / 15) % C, co = i / (15 * C);
+    const float w = J.src[i];
+    const int n = J.mode == 0 ? co : ci, r = J.mode == 0 ? ci : co, tap = J.mode == 0 ? t : 14 - t;
+    const int g = r >> 3, kc = (r >> 2) & 1, e = r & 3;
+    const long long o = ((((long long)g * 15 + tap) * 2 + kc) * C + n) * 4 + e;
+    const float hi = __uint_as_float(to_tf32(w));
+    J.dst[o] = hi;
+    J.dst[(long long)total + o] = __uint_as_float(to_tf32(w - hi));
+  }
+}
+
+#ifdef GNAS_TC_MARKS
+__device__ long long g_tc_marks[64];
+#define TC_MARK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_marks[i] = clock64(); } while (0)
+#else
+#define TC_MARK(i) do { } while (0)
+#endif
+
+// ------------------------------------------------------------------ the convolution
+struct TcJob {
+  const float* x; long long xbs;      // input [B][C][L] (forward: x or z1; data gradient: g)
+  const float* x2; long long x2bs;    // data gradient: raw BN input z of the conv output (dz = A*g + Bz*z + D), or null
+  const float* in_stat;               // forward T_BN_RELU: mean | rstd of the producer BN;  data gradient: A | Bz | D
+  const float* w;                     // packed hi | lo (k_pack_tc)
+  float* z; long long zbs;            // output [B][C][L]
+  double* acc;                        // forward / O_BNRELU_STORE: per-channel (sum, sumsq) or (sum v, sum v*z1)
+  const float* mref; long long mrbs;  // epilogue mask reference: x (O_RELU_ACC) or z1 (O_BNRELU_STORE)
+  const float* mstat;                 // mean | rstd of the inner BN (O_BNRELU_STORE)
+  int L, tin, omode;                  // tin: T_RELU / T_BN_RELU / -1 (affine dz); omode: O_STORE(+stats) / O_RELU_ACC / O_BNRELU_STORE
+};
+struct TcBatch { int n, B, C; TcJob j[kMaxDense]; };
+
+// How the 128 accumulator rows of a CTA map to (batch row, position).  Long sequences: 128 consecutive positions
+// of one batch row.  Short ones (L + 14 <= 64, e.g. the 42-position cell): several batch rows side by side,
+// each in a segment of L + 14 rows so that the tap shift never crosses into the neighbour's data.
+struct TcTiling {
+  int seg, nseg, tiles_per_row;
+  __host__ __device__ explicit TcTiling(int L) {
+    seg = L + 14;
+    nseg = seg <= 64 ? (128 - L) / seg + 1 : 1;
+    tiles_per_row = (L + 127) / 128;
+  }
+  __host__ __device__ int tiles(int B) const { return nseg > 1 ? (B + nseg - 1) / nseg : B * tiles_per_row; }
+};
+
+constexpr int kNAcc = 4;   // TMEM accumulators per tile: 3 take the hi*hi products in turn, 1 the cross terms
+
+// lane i ends with sum over the warp of a[i] (31 shuffles instead of 32 five-step reductions)
+__device__ __forceinline__ float warp_transpose_sum(float (&a)[32], int lane) {
+#pragma unroll
+  for (int lvl = 0; lvl < 5; ++lvl) {
+    const int off = 16 >> lvl;
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = upper ? a[k] : a[k + off];
+      const float keep = upper ? a[k + off] : a[k];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return a[0];
+}
+
+template <int C> struct TcCfg {
+  static constexpr int TT = C == 32 ? 5 : 3;               // taps per weight chunk
+  static constexpr int NST = C == 32 ? 4 : 3;              // weight stages in shared memory
+  static constexpr int W_CHUNK = TT * 2 * C * 4;           // floats of a chunk half (hi or lo)
+  static constexpr int A_HALF = (C / 4) * kRowsA * 4;      // floats of A_hi (= A_lo)
+  static constexpr size_t smem = sizeof(float) * (size_t)(2 * A_HALF + NST * 2 * W_CHUNK + 6 * C) + 128;
+};
+
+// Warp roles: thread 0 issues the MMAs, thread 32 streams the weight chunks (TMA bulk copies into an NST-deep
+// ring, full/empty mbarriers), warps 2-7 build the activation tile group by group (the MMAs of group g start
+// as soon as its 8 channels are in shared memory), all 8 warps run the epilogue.
+template <int C>
+__global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv15_tc(const __grid_constant__ TcBatch P) {
+  using Cfg = TcCfg<C>;
+  constexpr int G = C / 8;                                  // reduction groups of 8 channels
+  constexpr int TT = Cfg::TT, NTG = 15 / TT, NCH = G * NTG, NST = Cfg::NST;
+  constexpr int A_HALF = Cfg::A_HALF, W_CHUNK = Cfg::W_CHUNK;
+  constexpr int W_TAP = 2 * C * 4;                          // floats of one tap of one group (2 core-matrix columns)
+  constexpr uint32_t LBO_A = kRowsA * 16, SBO = 128, LBO_B = C * 16;
+  constexpr int TM_COLS = kNAcc * C;
+  constexpr int NLD = kTcThreads - 64;                      // activation-tile threads (warps 2..7)
+  const TcJob& J = P.j[blockIdx.z];
+  const int L = J.L;
+  const TcTiling tl(L);
+  const bool packed = tl.nseg > 1;
+  if ((int)blockIdx.x >= tl.tiles(P.B)) return;
+  const int b0 = packed ? blockIdx.x * tl.nseg : blockIdx.x / tl.tiles_per_row;
+  const int l0 = packed ? 0 : (blockIdx.x % tl.tiles_per_row) * 128;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (uniform datapath)
+  extern __shared__ __align__(128) unsigned char tc_smem_raw[];
+  float* A_hi = reinterpret_cast<float*>(tc_smem_raw);
+  float* A_lo = A_hi + A_HALF;
+  float* Wb = A_lo + A_HALF;                                // [NST][hi | lo][W_CHUNK]
+  float* ssum = Wb + NST * 2 * W_CHUNK;                     // [2][C]
+  float* sp = ssum + 2 * C;                                 // [3][C] input-transform parameters
+  float* smean = sp + 3 * C;                                // [C] mean of the inner BN (O_BNRELU_STORE)
+  __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_a[G], bar_done;
+  __shared__ uint32_t tmem_base_s;
+
+  TC_MARK(0);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+#pragma unroll
+    for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+#pragma unroll
+    for (int i = 0; i < G; ++i) mbar_init(&bar_a[i], NLD);
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 2 * C; i += kTcThreads) ssum[i] = 0.f;
+  {
+    const int np = J.tin == T_BN_RELU ? 2 * C : (J.tin < 0 && J.x2 ? 3 * C : 0);
+    for (int i = tid; i < np; i += kTcThreads) sp[i] = J.in_stat[i];
+    if (J.omode == O_BNRELU_STORE) for (int i = tid; i < C; i += kTcThreads) smean[i] = J.mstat[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  TC_MARK(1);
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 1) {
+    // ---- weight producer: chunk c = (group g, tap group) is W_CHUNK contiguous floats in each of the hi / lo halves
+    const float* whi = J.w;
+    const float* wlo = J.w + (long long)C * C * 15;
+    for (int c = 0; c < NCH; ++c) {
+      const int s = c % NST;
+      if (c >= NST) mbar_wait(&bar_empty[s], ((c / NST) - 1) & 1);
+      if (elect_one()) {
+        float* dst = Wb + s * 2 * W_CHUNK;
+        mbar_expect_tx(&bar_full[s], 2 * W_CHUNK * 4);
+        bulk_g2s(dst, whi + (long long)c * W_CHUNK, W_CHUNK * 4, &bar_full[s]);
+        bulk_g2s(dst + W_CHUNK, wlo + (long long)c * W_CHUNK, W_CHUNK * 4, &bar_full[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 0) {
+    // ---- MMA issuer: the whole warp runs the loop (descriptors stay in uniform registers), one elected lane issues
+    const uint32_t idesc = make_idesc(C);
+    const uint64_t ah0 = make_desc(smem_u32(A_hi), LBO_A, SBO), al0 = make_desc(smem_u32(A_lo), LBO_A, SBO);
+    const uint64_t bh0 = make_desc(smem_u32(Wb), LBO_B, SBO);
+    for (int c = 0; c < NCH; ++c) {
+      const int s = c % NST, g = c / NTG, tap0 = (c % NTG) * TT;
+      if (c % NTG == 0) { mbar_wait(&bar_a[g], 0); if (c == 0) TC_MARK(2); }
+      mbar_wait(&bar_full[s], (c / NST) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        // descriptor start-address field is (byte address >> 4) in the low 14 bits: offsets are plain adds
+        const uint64_t a_off = (uint64_t)(((uint32_t)(g * 2) * LBO_A + (uint32_t)tap0 * 16) >> 4);
+        const uint64_t ahc = ah0 + a_off, alc = al0 + a_off;
+        const uint64_t bhc = bh0 + (uint64_t)(((uint32_t)s * 2 * W_CHUNK * 4) >> 4), blc = bhc + (uint64_t)((W_CHUNK * 4) >> 4);
+#pragma unroll
+        for (int t = 0; t < TT; ++t) {
+          const uint64_t ah = ahc + t, al = alc + t;                                   // tap shift = +16 B per row
+          const uint64_t bh = bhc + (uint64_t)((t * W_TAP * 4) >> 4), bl = blc + (uint64_t)((t * W_TAP * 4) >> 4);
+          // hi*hi products rotate over accumulators 0..2 (fewer sequential fp32 accumulations per accumulator:
+          // the tensor core truncates when it adds), the small cross terms share accumulator 3
+          const int am = (c * TT + t) % 3;
+          mma_tf32(tmem_d + am * C, ah, bh, idesc, (uint32_t)(c | (t >= 3)));   // first touch overwrites
+          mma_tf32(tmem_d + 3 * C, ah, bl, idesc, (uint32_t)(c | t));
+          mma_tf32(tmem_d + 3 * C, al, bh, idesc, 1);
+        }
+        mma_commit(&bar_empty[s]);   // frees the stage when these MMAs have read it
+      }
+      __syncwarp();
+      if (c < 8) TC_MARK(8 + c);
+    }
+    if (elect_one()) mma_commit(&bar_done);
+    __syncwarp();
+    TC_MARK(3);
+  } else if (warp >= 2) {
+    // ---- activation tile: row p <-> (batch row, position - 7), transformed, split into tf32 hi / lo.
+    //      One item = 4 channels of one row = one 16-byte core-matrix row: conflict-free vector stores,
+    //      global loads coalesced along the row index; 4 items (16-32 loads) in flight per thread.
+    constexpr int NIT = (C / 4) * kRowsA, GI = 2 * kRowsA;   // items, items per group
+    constexpr int UN = 4;
+    const int tin = J.tin;
+    const bool affine = tin < 0 && J.x2 != nullptr;
+    int garr = 0;
+    for (int base = tid - 64; base < NIT; base += UN * NLD) {
+      float xv[UN][4], yv[UN][4];
+      int kcs[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int idx = base + u * NLD;
+        const int kc = idx / kRowsA, p = idx - kc * kRowsA;
+        kcs[u] = kc;
+        int bb, pos; bool ok;
+        if (packed) { const int sgi = p / tl.seg; bb = b0 + sgi; pos = p - sgi * tl.seg - 7; ok = sgi < tl.nseg && bb < P.B; }
+        else { bb = b0; pos = l0 - 7 + p; ok = p < 142; }
+        ok = ok && idx < NIT && pos >= 0 && pos < L;
+        const long long off = (long long)(4 * kc) * L + pos;
+        const float* xr = J.x + (long long)bb * J.xbs + off;
+        const float* yr = affine ? J.x2 + (long long)bb * J.x2bs + off : nullptr;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          xv[u][e] = ok ? xr[(long long)e * L] : 0.f;
+          yv[u][e] = (ok && affine) ? yr[(long long)e * L] : 0.f;
+        }
+        if (!ok) kcs[u] = -1 - kc;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int idx = base + u * NLD;
+        if (idx >= NIT) continue;
+        const bool ok = kcs[u] >= 0;
+        const int kc = ok ? kcs[u] : -1 - kcs[u];
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ch = 4 * kc + e;
+          float v = 0.f;
+          if (ok) {
+            if (tin == T_BN_RELU) { v = (xv[u][e] - sp[ch]) * sp[C + ch]; v = v > 0.f ? v : 0.f; }
+            else if (tin == T_RELU) v = xv[u][e] > 0.f ? xv[u][e] : 0.f;
+            else if (affine) v = fmaf(sp[ch], xv[u][e], fmaf(sp[C + ch], yv[u][e], sp[2 * C + ch]));
+            else v = xv[u][e];
+          }
+          hi[e] = __uint_as_float(to_tf32(v));
+          lo[e] = __uint_as_float(to_tf32(v - hi[e]));
+        }
+        *reinterpret_cast<float4*>(A_hi + (long long)idx * 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(A_lo + (long long)idx * 4) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      // groups whose items this thread has all written: publish (generic -> async proxy fence, then arrive)
+      const int nxt = base + UN * NLD;
+      while (garr < G && (garr + 1) * GI <= nxt) { fence_async_smem(); mbar_arrive(&bar_a[garr]); ++garr; }
+    }
+    while (garr < G) { fence_async_smem(); mbar_arrive(&bar_a[garr]); ++garr; }
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM -> registers -> global (+ per-channel statistics)
+  mbar_wait(&bar_done, 0);
+  tc_fence_after();
+  TC_MARK(4);
+  {
+    const int row = 32 * (warp & 3) + lane;
+    int bb, l; bool valid;
+    if (packed) { const int sgi = row / tl.seg; bb = b0 + sgi; l = row - sgi * tl.seg; valid = sgi < tl.nseg && bb < P.B && l < L; }
+    else { bb = b0; l = l0 + row; valid = l < L; }
+    constexpr int CPW = C >= 64 ? C / 2 : 32;             // columns per warp (two warps share a TMEM lane quarter)
+    const int col_base = C >= 64 ? (warp >> 2) * CPW : 0;
+    const bool warp_on = C >= 64 || warp < 4;
+    float* zrow = J.z + (long long)bb * J.zbs + l;
+    const float* mrow = J.mref ? J.mref + (long long)bb * J.mrbs + l : nullptr;
+    const int omode = J.omode;
+    const bool stats = J.acc != nullptr;
+    if (warp_on) {
+#pragma unroll 1
+      for (int c0 = col_base; c0 < col_base + CPW; c0 += 32) {
+        float v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0;
+        tmem_ld32(taddr, v);
+#pragma unroll
+        for (int a = 1; a < kNAcc; ++a) {
+          float t[32];
+          tmem_ld32(taddr + a * C, t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += t[i];
+        }
+        float q[32];
+        if (omode == O_STORE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = valid ? v[i] : 0.f;
+            if (valid) zrow[(long long)(c0 + i) * L] = v[i];
+            q[i] = v[i] * v[i];
+          }
+        } else if (omode == O_RELU_ACC) {
+          float xr[32], old[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            xr[i] = valid ? mrow[(long long)(c0 + i) * L] : 0.f;
+            old[i] = valid ? zrow[(long long)(c0 + i) * L] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (valid && xr[i] > 0.f) zrow[(long long)(c0 + i) * L] = old[i] + v[i];
+        } else {   // O_BNRELU_STORE
+          float zi[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) zi[i] = valid ? mrow[(long long)(c0 + i) * L] : 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = (valid && zi[i] > smean[c0 + i]) ? v[i] : 0.f;
+            if (valid) zrow[(long long)(c0 + i) * L] = v[i];
+            q[i] = v[i] * zi[i];
+          }
+        }
+        if (stats && omode != O_RELU_ACC) {
+          const float s = warp_transpose_sum(v, lane), qq = warp_transpose_sum(q, lane);
+          atomicAdd(&ssum[c0 + lane], s);
+          atomicAdd(&ssum[C + c0 + lane], qq);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  TC_MARK(5);
+  if (J.acc != nullptr)
+    for (int i = tid; i < 2 * C; i += kTcThreads) atomicAdd(&J.acc[i], (double)ssum[i]);
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TM_COLS) : "memory");
+  }
+  TC_MARK(6);
+}
+
+template <int C>
+static size_t tc_smem_bytes() { return TcCfg<C>::smem; }
+
+static inline bool tc_supported(int C) { return C == 32 || C == 64 || C == 128; }
+
+static int launch_conv15_tc(TcBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  int tiles = 0;
+  for (int i = 0; i < b.n; ++i) { const int t = TcTiling(b.j[i].L).tiles(b.B); tiles = t > tiles ? t : tiles; }
+  dim3 grid(tiles, 1, b.n);
+#define GNAS_TC_CASE(c)                                                                                   \
+  if (b.C == c) {                                                                                         \
+    const size_t smem = tc_smem_bytes<c>();                                                               \
+    static bool prepared = false;                                                                         \
+    if (!prepared) { cudaFuncSetAttribute(k_conv15_tc<c>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); prepared = true; } \
+    prof_before("k_conv15_tc<" #c ">", "", st);                                                           \
+    k_conv15_tc<c><<<grid, dim3(kTcThreads), smem, st>>>(b);                                              \
+    prof_after(st);                                                                                       \
+  } else
+  GNAS_TC_CASE(32) GNAS_TC_CASE(64) GNAS_TC_CASE(128) { set_error("conv15_tc: unsupported channel count"); return GNAS_ERR_UNSUPPORTED; }
+#undef GNAS_TC_CASE
+  b.n = 0;
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace gnas
+#endif  // !GNAS_EMUL

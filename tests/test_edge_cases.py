@@ -31,6 +31,12 @@ def _oracle_mixed(m, x, w, switch, stride, P, skip_mask=None, p=0.0):
     (3, 8, 30, 2, [False, False, False, True, False, False, False, False, False]),   # strided skip only
     (4, 8, 64, 1, [True, False, False, True, False, False, False, False, False]),    # none + identity
     (2, 32, 250, 1, [False, True, True, False, True, False, False, True, False]),
+    # conv_15 at the channel counts the tcgen05 kernel takes (C = 32 / 64 / 128, stride-1 convolutions):
+    (3, 32, 250, 1, [False] * 8 + [True]),                       # two position tiles, ragged tail
+    (2, 32, 300, 1, [True] + [False] * 7 + [True]),              # three tiles
+    (2, 64, 125, 1, [False] * 8 + [True]),                       # one partial tile (cell 4 geometry)
+    (3, 128, 42, 1, [False] * 8 + [True]),                       # cell 5 geometry
+    (2, 64, 125, 2, [False] * 8 + [True]),                       # strided first conv (SIMT) + stride-1 second conv
 ])
 def test_mixedop_shapes(backend, B, C, L, stride, switch):
     torch.manual_seed(B * 100 + L)

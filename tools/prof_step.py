@@ -27,3 +27,13 @@ for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     out = st.step(xt, yt, xv, yv)
 torch.cuda.synchronize()
 print("ok", float(out[1]))
+if os.environ.get("GNAS_REPORT"):
+    # event-bracketed per-kernel totals of one eager step (inflated for tiny kernels; fine for the big ones)
+    from genome_nas_b200 import _lib
+    _lib.profile(True)
+    out = st.step(xt, yt, xv, yv)
+    torch.cuda.synchronize()
+    rep = _lib.profile_report()
+    _lib.profile(False)
+    for k, (n, ms) in sorted(rep.items(), key=lambda kv: -kv[1][1])[:int(os.environ["GNAS_REPORT"])]:
+        print(f"{ms:9.3f} ms {n:6d} x {1e3 * ms / n:9.1f} us  {k}")
