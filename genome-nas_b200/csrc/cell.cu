@@ -33,7 +33,7 @@ struct OpPlan {
   long long t[4] = {-1, -1, -1, -1};   // forward tensors in ws
   int slot[2] = {-1, -1};   // BN slots
   long long pk[2] = {-1, -1};          // packed forward weights in ws
-  long long pkb[2] = {-1, -1};         // packed backward weights in scratch (conv_15 only)
+  long long pkb[2] = {-1, -1};         // packed backward weights in scratch (conv_15; pointwise on the tensor-core path)
 };
 struct EdgePlan {
   int node = 0, src = 0, stride = 1, Lin = 0;
@@ -72,16 +72,17 @@ inline bool tc_on(int C, int stride) {
   return tc_enabled() && stride == 1 && tc::tc_supported(C);
 #endif
 }
-// debugging aid: GNAS_TC_PART bit 0 = forward, bit 1 = data gradient of the second conv, bit 2 = of the first conv
+// debugging aid: GNAS_TC_PART bit 0 = conv_15 forward, bit 1 / 2 = data gradient of its second / first conv,
+// bit 3 = pointwise convs (forward and data gradient)
 inline bool tc_part(int bit) {
   static int v = -1;
-  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 7; }
+  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 15; }
   return (v >> bit) & 1;
 }
 #ifndef GNAS_EMUL
 // the same jobs, handed to the tensor-core kernel
-int launch_conv15_fwd_tc(DenseBatch& db, cudaStream_t st) {
-  tc::TcBatch tb; tb.n = 0; tb.B = db.B; tb.C = db.Cout;
+int launch_conv_fwd_tc(DenseBatch& db, int KW, cudaStream_t st) {
+  tc::TcBatch tb; tb.n = 0; tb.B = db.B; tb.C = db.Cout; tb.KW = KW;
   for (int i = 0; i < db.n; ++i) {
     const DenseJob& j = db.j[i];
     tc::TcJob& t = tb.j[tb.n++];
@@ -90,10 +91,10 @@ int launch_conv15_fwd_tc(DenseBatch& db, cudaStream_t st) {
     t.L = j.Lout; t.tin = j.tin; t.omode = O_STORE;
   }
   db.n = 0;
-  return tc::launch_conv15_tc(tb, st);
+  return tc::launch_conv_tc(tb, st);
 }
-int launch_conv15_dx_tc(DxBatch& xb, cudaStream_t st) {
-  tc::TcBatch tb; tb.n = 0; tb.B = xb.B; tb.C = xb.Cin;
+int launch_conv_dx_tc(DxBatch& xb, int KW, cudaStream_t st) {
+  tc::TcBatch tb; tb.n = 0; tb.B = xb.B; tb.C = xb.Cin; tb.KW = KW;
   for (int i = 0; i < xb.n; ++i) {
     const DxJob& j = xb.j[i];
     tc::TcJob& t = tb.j[tb.n++];
@@ -103,7 +104,7 @@ int launch_conv15_dx_tc(DxBatch& xb, cudaStream_t st) {
     t.L = j.Lo; t.tin = -1; t.omode = j.omode;
   }
   xb.n = 0;
-  return tc::launch_conv15_tc(tb, st);
+  return tc::launch_conv_tc(tb, st);
 }
 void pack_tc(tc::TcPackBatch& pb, cudaStream_t st) {
   if (pb.n == 0) return;
@@ -111,11 +112,13 @@ void pack_tc(tc::TcPackBatch& pb, cudaStream_t st) {
   pb.n = 0;
 }
 #else
-int launch_conv15_fwd_tc(DenseBatch&, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
-int launch_conv15_dx_tc(DxBatch&, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
+int launch_conv_fwd_tc(DenseBatch&, int, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
+int launch_conv_dx_tc(DxBatch&, int, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
 #endif
 inline bool tc_fwd_on(int C, int stride) { return tc_on(C, stride) && tc_part(0); }
 inline bool tc_dx_on(int C, int stride, int conv) { return tc_on(C, stride) && tc_part(conv == 1 ? 1 : 2); }
+inline bool tc_pw_on(int C) { return tc_on(C, 1) && tc_part(3); }
+inline long long pw_pack_floats(int C) { return (long long)C * C * (tc_pw_on(C) ? 2 : 1); }
 inline long long conv15_pack_floats(int C) { return (long long)C * C * 15 * (tc_on(C, 1) ? 2 : 1); }
 
 int validate(const GnasCellDesc* d) {
@@ -190,8 +193,8 @@ void make_plan(const GnasCellDesc* d, CellPlan& P) {
       switch (k) {
         case GNAS_MAX_POOL: case GNAS_AVG_POOL: nt = 1; break;
         case GNAS_SKIP: if (E.stride > 1) { nt = 1; npk[0] = C * C; } break;
-        case GNAS_SEP15: case GNAS_SEP9: nt = 4; npk[0] = npk[1] = C * C; break;
-        case GNAS_DIL15: case GNAS_DIL9: nt = 2; npk[0] = C * C; break;
+        case GNAS_SEP15: case GNAS_SEP9: nt = 4; npk[0] = npk[1] = (int)pw_pack_floats(C); break;
+        case GNAS_DIL15: case GNAS_DIL9: nt = 2; npk[0] = (int)pw_pack_floats(C); break;
         case GNAS_CONV15: nt = 2; npk[0] = npk[1] = (int)conv15_pack_floats(C); break;
         default: break;
       }
@@ -215,6 +218,14 @@ void make_plan(const GnasCellDesc* d, CellPlan& P) {
   for (int e = 0; e < d->n_edges; ++e) {
     OpPlan& O = P.e[e].op[GNAS_CONV15];
     if (O.on) for (int i = 0; i < 2; ++i) { O.pkb[i] = o; o += al4(conv15_pack_floats(C)); }
+    if (tc_pw_on(C)) {   // tensor-core data gradient of the pointwise convs: transposed hi | lo packs
+      const int ks[4] = {GNAS_SEP15, GNAS_SEP9, GNAS_DIL15, GNAS_DIL9};
+      for (int v = 0; v < 4; ++v) {
+        OpPlan& Q = P.e[e].op[ks[v]];
+        if (!Q.on) continue;
+        for (int i = 0; i < (v < 2 ? 2 : 1); ++i) { Q.pkb[i] = o; o += al4(2LL * C * C); }
+      }
+    }
   }
   P.bwd_total = o;
 }
@@ -310,6 +321,7 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     }
     c.rc |= launch_dense_fwd(1, S, db, c.st);
   }
+  auto pw_fwd = [&](DenseBatch& b) { return tc_pw_on(C) ? launch_conv_fwd_tc(b, 1, c.st) : launch_dense_fwd(1, 1, b, c.st); };
   // depthwise stage 1 (sep: dilation 1, dil: dilation 2)
   const int dwk[4] = {GNAS_SEP15, GNAS_SEP9, GNAS_DIL15, GNAS_DIL9};
   const int dwK[4] = {15, 9, 15, 9}, dwD[4] = {1, 1, 2, 2}, dwP[4] = {7, 4, 14, 8};
@@ -336,10 +348,10 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
       j.z = c.T(e, dwk[v], 1); j.zbs = obs; j.acc = train ? c.acc(O.slot[0]) : nullptr;
       j.Cin = C; j.Lin = Lo; j.Lout = Lo; j.tin = T_NONE;
       fin_add(e, dwk[v], 0);
-      if (db.n == kMaxDense) c.rc |= launch_dense_fwd(1, 1, db, c.st);
+      if (db.n == kMaxDense) c.rc |= pw_fwd(db);
     }
   }
-  c.rc |= launch_dense_fwd(1, 1, db, c.st);
+  c.rc |= pw_fwd(db);
   // conv_15 stage 1
   db.pad = 7;
   for (int i = 0; i < ne; ++i) {
@@ -352,7 +364,7 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     j.Cin = C; j.Lin = Lin; j.Lout = Lo; j.tin = T_RELU;
     fin_add(e, GNAS_CONV15, 0);
   }
-  c.rc |= tc_fwd_on(C, S) ? launch_conv15_fwd_tc(db, c.st) : launch_dense_fwd(15, S, db, c.st);
+  c.rc |= tc_fwd_on(C, S) ? launch_conv_fwd_tc(db, 15, c.st) : launch_dense_fwd(15, S, db, c.st);
   finalize(c, fs, fc, fr, nf);
   nf = 0;
   // ---- stage 2 (sep_conv second half, conv_15 second conv) reads BN+ReLU of stage 1 on the fly
@@ -382,7 +394,7 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
       fin_add(e, dwk[v], 1);
     }
   }
-  c.rc |= launch_dense_fwd(1, 1, db, c.st);
+  c.rc |= pw_fwd(db);
   db.pad = 7;
   for (int i = 0; i < ne; ++i) {
     const int e = edges[i];
@@ -394,7 +406,7 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     j.Cin = C; j.Lin = Lo; j.Lout = Lo; j.tin = T_BN_RELU;
     fin_add(e, GNAS_CONV15, 1);
   }
-  c.rc |= tc_fwd_on(C, 1) ? launch_conv15_fwd_tc(db, c.st) : launch_dense_fwd(15, 1, db, c.st);
+  c.rc |= tc_fwd_on(C, 1) ? launch_conv_fwd_tc(db, 15, c.st) : launch_dense_fwd(15, 1, db, c.st);
   finalize(c, fs, fc, fr, nf);
 }
 
@@ -453,15 +465,25 @@ void pack_forward(Ctx& c) {
       const OpPlan& O = E.op[k];
       if (!O.on) continue;
       if (k == GNAS_SKIP && E.stride > 1) add(c.W(e, k, 0), c.ws + O.pk[0], C, C, 1, 0);
-      if (k == GNAS_SEP15 || k == GNAS_SEP9) { add(c.W(e, k, 1), c.ws + O.pk[0], C, C, 1, 0); add(c.W(e, k, 3), c.ws + O.pk[1], C, C, 1, 0); }
-      if (k == GNAS_DIL15 || k == GNAS_DIL9) add(c.W(e, k, 1), c.ws + O.pk[0], C, C, 1, 0);
+      if (k == GNAS_SEP15 || k == GNAS_SEP9 || k == GNAS_DIL15 || k == GNAS_DIL9) {
+        const int npw = (k == GNAS_SEP15 || k == GNAS_SEP9) ? 2 : 1;
+        for (int i = 0; i < npw; ++i) {
+          const float* src = c.W(e, k, i == 0 ? 1 : 3);
+          if (!tc_pw_on(C)) { add(src, c.ws + O.pk[i], C, C, 1, 0); continue; }
+#ifndef GNAS_EMUL
+          tc::TcPackJob& t = tp.j[tp.n++];
+          t.src = src; t.dst = c.ws + O.pk[i]; t.C = C; t.mode = 0; t.KW = 1;
+          if (tp.n == 64) pack_tc(tp, c.st);
+#endif
+        }
+      }
       if (k == GNAS_CONV15) {
         for (int i = 0; i < 2; ++i) {
           const int cs = i == 0 ? E.stride : 1;
           if (!tc_fwd_on(C, cs)) { add(c.W(e, k, i), c.ws + O.pk[i], C, C, 15, 0); continue; }
 #ifndef GNAS_EMUL
           tc::TcPackJob& t = tp.j[tp.n++];
-          t.src = c.W(e, k, i); t.dst = c.ws + O.pk[i]; t.C = C; t.mode = 0;
+          t.src = c.W(e, k, i); t.dst = c.ws + O.pk[i]; t.C = C; t.mode = 0; t.KW = 15;
           if (tp.n == 64) pack_tc(tp, c.st);
 #endif
         }
@@ -592,6 +614,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     auto tmp = [&](int i, int which) { return c.scratch + c.P.tmp[is[i]][which]; };
     DxBatch xb; xb.n = 0; xb.B = B; xb.Cin = C; xb.pad = 0;
     WgBatch gb; gb.n = 0; gb.B = B; gb.Cout = C;
+    auto pw_dx = [&](DxBatch& b) { return tc_pw_on(C) ? launch_conv_dx_tc(b, 1, c.st) : launch_dense_dx(1, 1, b, c.st); };
     // -- strided skip (FactorizedReduce): dx + dW
     if (S > 1) {
       for (int i = 0; i < n2; ++i) {
@@ -622,7 +645,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         const bool sep = v < 2;
         DxJob& j = xb.j[xb.n++];
         j.g = g; j.gbs = gbs; j.z = c.T(e, dwk[v], sep ? 3 : 1); j.zbs = obs; j.coef = c.coef(O.slot[sep ? 1 : 0]);
-        j.wt = c.W(e, dwk[v], sep ? 3 : 1); j.out = tmp(i, tmp0[v]); j.obs = obs;
+        j.wt = tc_pw_on(C) ? c.scratch + O.pkb[sep ? 1 : 0] : c.W(e, dwk[v], sep ? 3 : 1); j.out = tmp(i, tmp0[v]); j.obs = obs;
         j.xin = nullptr; j.xibs = 0; j.xin_stat = nullptr; j.bacc = nullptr;
         j.Cout = C; j.Lo = Lo; j.Lin = Lo; j.omode = O_STORE;
         if (need_wgrad) {
@@ -631,10 +654,10 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
           w.r = c.T(e, dwk[v], sep ? 2 : 0); w.rbs = obs; w.r_stat = nullptr; w.dw = c.dW(e, dwk[v], sep ? 3 : 1);
           w.Cin = C; w.Lo = Lo; w.Lin = Lo; w.tin = T_NONE;
         }
-        if (xb.n == kMaxDense) { c.rc |= launch_dense_dx(1, 1, xb, c.st); c.rc |= launch_pw_wgrad(1, gb, c.st); }
+        if (xb.n == kMaxDense) { c.rc |= pw_dx(xb); c.rc |= launch_pw_wgrad(1, gb, c.st); }
       }
     }
-    c.rc |= launch_dense_dx(1, 1, xb, c.st);
+    c.rc |= pw_dx(xb);
     c.rc |= launch_pw_wgrad(1, gb, c.st);
     // -- depthwise: sep stage 2 (-> dyh1 + inner BN sums), dil (-> dX)
     for (int v = 0; v < 4; ++v) {
@@ -676,7 +699,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         w.Cin = C; w.Lo = Lo; w.Lin = Lo; w.tin = T_BN_RELU;
       }
     }
-    c.rc |= tc_dx_on(C, 1, 1) ? launch_conv15_dx_tc(xb, c.st) : launch_dense_dx(15, 1, xb, c.st);
+    c.rc |= tc_dx_on(C, 1, 1) ? launch_conv_dx_tc(xb, 15, c.st) : launch_dense_dx(15, 1, xb, c.st);
     c.rc |= launch_conv_wgrad(15, 1, 7, gb, c.st);
     // -- inner BN coefficients (w = 1)
     {
@@ -697,7 +720,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         if (!O.on) continue;
         DxJob& j = xb.j[xb.n++];
         j.g = tmp(i, tmp0[v] + 1); j.gbs = obs; j.z = c.T(e, dwk[v], 1); j.zbs = obs; j.coef = c.coef(O.slot[0]);
-        j.wt = c.W(e, dwk[v], 1); j.out = tmp(i, tmp0[v] + 2); j.obs = obs;
+        j.wt = tc_pw_on(C) ? c.scratch + O.pkb[0] : c.W(e, dwk[v], 1); j.out = tmp(i, tmp0[v] + 2); j.obs = obs;
         j.xin = nullptr; j.xibs = 0; j.xin_stat = nullptr; j.bacc = nullptr;
         j.Cout = C; j.Lo = Lo; j.Lin = Lo; j.omode = O_STORE;
         if (need_wgrad) {
@@ -708,7 +731,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         }
       }
     }
-    c.rc |= launch_dense_dx(1, 1, xb, c.st);
+    c.rc |= pw_dx(xb);
     c.rc |= launch_pw_wgrad(1, gb, c.st);
     for (int v = 0; v < 2; ++v) {
       DwBwdBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = dwP[v];
@@ -741,7 +764,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         w.Cin = C; w.Lo = Lo; w.Lin = Lin; w.tin = T_RELU;
       }
     }
-    c.rc |= tc_dx_on(C, S, 0) ? launch_conv15_dx_tc(xb, c.st) : launch_dense_dx(15, S, xb, c.st);
+    c.rc |= tc_dx_on(C, S, 0) ? launch_conv_dx_tc(xb, 15, c.st) : launch_dense_dx(15, S, xb, c.st);
     c.rc |= launch_conv_wgrad(15, S, 7, gb, c.st);
   }
 }
@@ -804,7 +827,7 @@ void pack_backward(Ctx& c) {
       if (tc_dx_on(C, cs, i)) {
 #ifndef GNAS_EMUL
         tc::TcPackJob& t = tp.j[tp.n++];
-        t.src = c.W(e, GNAS_CONV15, i); t.dst = c.scratch + O.pkb[i]; t.C = C; t.mode = 1;
+        t.src = c.W(e, GNAS_CONV15, i); t.dst = c.scratch + O.pkb[i]; t.C = C; t.mode = 1; t.KW = 15;
         if (tp.n == 64) pack_tc(tp, c.st);
 #endif
         continue;
@@ -814,6 +837,19 @@ void pack_backward(Ctx& c) {
     }
   }
 #ifndef GNAS_EMUL
+  if (tc_pw_on(C)) {
+    const int ks[4] = {GNAS_SEP15, GNAS_SEP9, GNAS_DIL15, GNAS_DIL9};
+    for (int e = 0; e < c.P.n_edges; ++e)
+      for (int v = 0; v < 4; ++v) {
+        const OpPlan& O = c.P.e[e].op[ks[v]];
+        if (!O.on) continue;
+        for (int i = 0; i < (v < 2 ? 2 : 1); ++i) {
+          tc::TcPackJob& t = tp.j[tp.n++];
+          t.src = c.W(e, ks[v], i == 0 ? 1 : 3); t.dst = c.scratch + O.pkb[i]; t.C = C; t.mode = 1; t.KW = 1;
+          if (tp.n == 64) pack_tc(tp, c.st);
+        }
+      }
+  }
   pack_tc(tp, c.st);
 #endif
   if (pb.n) GNAS_LAUNCH(k_pack_weights, dim3(8, pb.n), dim3(256), 0, c.st, pb);

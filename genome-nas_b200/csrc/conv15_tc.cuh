@@ -1,4 +1,5 @@
-// conv_15 (dense 15-tap Conv1d, stride 1, C -> C) on the 5th-generation tensor cores:
+// Dense stride-1 Conv1d C -> C with 15 taps (conv_15) or 1 tap (the pointwise convs of sep_conv / dil_conv,
+// operations_14_9.py:36-64) on the 5th-generation tensor cores:
 // implicit GEMM  D[128 positions][C_out] += A_tap[128][8 ch] * B_tap[C_out][8 ch]^T  issued as
 // tcgen05.mma kind::tf32 with the accumulator in TMEM, error-compensated 3xTF32
 // (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate) because plain TF32 destroys the gradients
@@ -17,7 +18,6 @@
 namespace gnas {
 namespace tc {
 
-constexpr int kRowsA = 144;          // 128 output rows + 14 halo rows (+2 pad): rows of one 4-channel group
 constexpr int kTcThreads = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,18 +94,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 // ------------------------------------------------------------------ weight packing (hi | lo, tensor-core layout)
 // dst[half][g][tap][kc][n][e]  (g: group of 8 reduction channels, kc: 4-channel core matrix, n: output row, e: 0..3)
 // mode 0 (forward): n = co, reduction channel = ci, tap as is;   mode 1 (data gradient): n = ci, reduction = co,
-// tap flipped (out[m] = sum_t W[.,.,t] dz[m + 7 - t]  ==  conv with taps t' = 14 - t).
-struct TcPackJob { const float* src; float* dst; int C, mode; };
+// tap flipped (out[m] = sum_t W[.,.,t] dz[m + pad - t]  ==  conv with taps t' = KW - 1 - t).
+struct TcPackJob { const float* src; float* dst; int C, mode, KW; };
 struct TcPackBatch { int n; TcPackJob j[64]; };
 static __global__ void __launch_bounds__(256) k_pack_tc(const __grid_constant__ TcPackBatch P) {
   const TcPackJob& J = P.j[blockIdx.y];
-  const int C = J.C, total = C * C * 15;
+  const int C = J.C, KW = J.KW, total = C * C * KW;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int t = i % 15, ci = (i / 15) % C, co = i / (15 * C);
+    const int t = i % KW, ci = (i / KW) % C, co = i / (KW * C);
     const float w = J.src[i];
-    const int n = J.mode == 0 ? co : ci, r = J.mode == 0 ? ci : co, tap = J.mode == 0 ? t : 14 - t;
+    const int n = J.mode == 0 ? co : ci, r = J.mode == 0 ? ci : co, tap = J.mode == 0 ? t : KW - 1 - t;
     const int g = r >> 3, kc = (r >> 2) & 1, e = r & 3;
-    const long long o = ((((long long)g * 15 + tap) * 2 + kc) * C + n) * 4 + e;
+    const long long o = ((((long long)g * KW + tap) * 2 + kc) * C + n) * 4 + e;
     const float hi = __uint_as_float(to_tf32(w));
     J.dst[o] = hi;
     J.dst[(long long)total + o] = __uint_as_float(to_tf32(w - hi));
@@ -131,15 +131,15 @@ struct TcJob {
   const float* mstat;                 // mean | rstd of the inner BN (O_BNRELU_STORE)
   int L, tin, omode;                  // tin: T_RELU / T_BN_RELU / -1 (affine dz); omode: O_STORE(+stats) / O_RELU_ACC / O_BNRELU_STORE
 };
-struct TcBatch { int n, B, C; TcJob j[kMaxDense]; };
+struct TcBatch { int n, B, C, KW; TcJob j[kMaxDense]; };
 
 // How the 128 accumulator rows of a CTA map to (batch row, position).  Long sequences: 128 consecutive positions
-// of one batch row.  Short ones (L + 14 <= 64, e.g. the 42-position cell): several batch rows side by side,
-// each in a segment of L + 14 rows so that the tap shift never crosses into the neighbour's data.
+// of one batch row.  Short ones (L + KW - 1 <= 64, e.g. the 42-position cell): several batch rows side by side,
+// each in a segment of L + KW - 1 rows so that the tap shift never crosses into the neighbour's data.
 struct TcTiling {
   int seg, nseg, tiles_per_row;
-  __host__ __device__ explicit TcTiling(int L) {
-    seg = L + 14;
+  __host__ __device__ TcTiling(int L, int KW) {
+    seg = L + KW - 1;
     nseg = seg <= 64 ? (128 - L) / seg + 1 : 1;
     tiles_per_row = (L + 127) / 128;
   }
@@ -164,30 +164,34 @@ __device__ __forceinline__ float warp_transpose_sum(float (&a)[32], int lane) {
   return a[0];
 }
 
-template <int C> struct TcCfg {
-  static constexpr int TT = C == 32 ? 5 : 3;               // taps per weight chunk
-  static constexpr int NST = C == 32 ? 4 : 3;              // weight stages in shared memory
-  static constexpr int W_CHUNK = TT * 2 * C * 4;           // floats of a chunk half (hi or lo)
-  static constexpr int A_HALF = (C / 4) * kRowsA * 4;      // floats of A_hi (= A_lo)
+template <int C, int KW> struct TcCfg {
+  static constexpr int ROWS = KW == 1 ? 128 : 144;         // A rows per 4-channel group: 128 outputs + KW-1 halo (+2 pad)
+  static constexpr int NU = (C / 8) * KW;                  // MMA units: (group of 8 reduction channels, tap)
+  static constexpr int TT = KW == 1 ? (C == 128 ? 4 : C / 8) : (C == 32 ? 5 : 3);   // units per weight chunk
+  static constexpr int NST = KW == 1 ? (C == 128 ? 2 : 1) : (C == 32 ? 4 : 3);      // weight stages in shared memory
+  static constexpr int NCH = NU / TT;
+  static constexpr int W_UNIT = 2 * C * 4;                 // floats of one unit (2 core-matrix columns x C rows), hi or lo
+  static constexpr int W_CHUNK = TT * W_UNIT;
+  static constexpr int A_HALF = (C / 4) * ROWS * 4;        // floats of A_hi (= A_lo)
   static constexpr size_t smem = sizeof(float) * (size_t)(2 * A_HALF + NST * 2 * W_CHUNK + 6 * C) + 128;
+  static_assert(NU % TT == 0, "chunks must tile the units");
 };
 
 // Warp roles: thread 0 issues the MMAs, thread 32 streams the weight chunks (TMA bulk copies into an NST-deep
 // ring, full/empty mbarriers), warps 2-7 build the activation tile group by group (the MMAs of group g start
 // as soon as its 8 channels are in shared memory), all 8 warps run the epilogue.
-template <int C>
-__global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv15_tc(const __grid_constant__ TcBatch P) {
-  using Cfg = TcCfg<C>;
+template <int C, int KW>
+__global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const __grid_constant__ TcBatch P) {
+  using Cfg = TcCfg<C, KW>;
   constexpr int G = C / 8;                                  // reduction groups of 8 channels
-  constexpr int TT = Cfg::TT, NTG = 15 / TT, NCH = G * NTG, NST = Cfg::NST;
-  constexpr int A_HALF = Cfg::A_HALF, W_CHUNK = Cfg::W_CHUNK;
-  constexpr int W_TAP = 2 * C * 4;                          // floats of one tap of one group (2 core-matrix columns)
-  constexpr uint32_t LBO_A = kRowsA * 16, SBO = 128, LBO_B = C * 16;
+  constexpr int TT = Cfg::TT, NCH = Cfg::NCH, NST = Cfg::NST, ROWS = Cfg::ROWS, HALO = (KW - 1) / 2;
+  constexpr int A_HALF = Cfg::A_HALF, W_CHUNK = Cfg::W_CHUNK, W_UNIT = Cfg::W_UNIT;
+  constexpr uint32_t LBO_A = ROWS * 16, SBO = 128, LBO_B = C * 16;
   constexpr int TM_COLS = kNAcc * C;
   constexpr int NLD = kTcThreads - 64;                      // activation-tile threads (warps 2..7)
   const TcJob& J = P.j[blockIdx.z];
   const int L = J.L;
-  const TcTiling tl(L);
+  const TcTiling tl(L, KW);
   const bool packed = tl.nseg > 1;
   if ((int)blockIdx.x >= tl.tiles(P.B)) return;
   const int b0 = packed ? blockIdx.x * tl.nseg : blockIdx.x / tl.tiles_per_row;
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv15_tc(cons
   if (warp == 1) {
     // ---- weight producer: chunk c = (group g, tap group) is W_CHUNK contiguous floats in each of the hi / lo halves
     const float* whi = J.w;
-    const float* wlo = J.w + (long long)C * C * 15;
+    const float* wlo = J.w + (long long)C * C * KW;
     for (int c = 0; c < NCH; ++c) {
       const int s = c % NST;
       if (c >= NST) mbar_wait(&bar_empty[s], ((c / NST) - 1) & 1);
@@ -249,25 +253,28 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv15_tc(cons
     const uint32_t idesc = make_idesc(C);
     const uint64_t ah0 = make_desc(smem_u32(A_hi), LBO_A, SBO), al0 = make_desc(smem_u32(A_lo), LBO_A, SBO);
     const uint64_t bh0 = make_desc(smem_u32(Wb), LBO_B, SBO);
+    int gw = 0;                    // activation groups already waited for
     for (int c = 0; c < NCH; ++c) {
-      const int s = c % NST, g = c / NTG, tap0 = (c % NTG) * TT;
-      if (c % NTG == 0) { mbar_wait(&bar_a[g], 0); if (c == 0) TC_MARK(2); }
+      const int s = c % NST;
+      const int g_last = (c * TT + TT - 1) / KW;
+      while (gw <= g_last) { mbar_wait(&bar_a[gw], 0); ++gw; }
+      if (c == 0) TC_MARK(2);
       mbar_wait(&bar_full[s], (c / NST) & 1);
       tc_fence_after();
       if (elect_one()) {
         // descriptor start-address field is (byte address >> 4) in the low 14 bits: offsets are plain adds
-        const uint64_t a_off = (uint64_t)(((uint32_t)(g * 2) * LBO_A + (uint32_t)tap0 * 16) >> 4);
-        const uint64_t ahc = ah0 + a_off, alc = al0 + a_off;
         const uint64_t bhc = bh0 + (uint64_t)(((uint32_t)s * 2 * W_CHUNK * 4) >> 4), blc = bhc + (uint64_t)((W_CHUNK * 4) >> 4);
 #pragma unroll
         for (int t = 0; t < TT; ++t) {
-          const uint64_t ah = ahc + t, al = alc + t;                                   // tap shift = +16 B per row
-          const uint64_t bh = bhc + (uint64_t)((t * W_TAP * 4) >> 4), bl = blc + (uint64_t)((t * W_TAP * 4) >> 4);
+          const int unit = c * TT + t, g = unit / KW, tap = unit - g * KW;
+          const uint64_t a_off = (uint64_t)(((uint32_t)(g * 2) * LBO_A + (uint32_t)tap * 16) >> 4);   // tap shift = +16 B per row
+          const uint64_t ah = ah0 + a_off, al = al0 + a_off;
+          const uint64_t bh = bhc + (uint64_t)((t * W_UNIT * 4) >> 4), bl = blc + (uint64_t)((t * W_UNIT * 4) >> 4);
           // hi*hi products rotate over accumulators 0..2 (fewer sequential fp32 accumulations per accumulator:
           // the tensor core truncates when it adds), the small cross terms share accumulator 3
-          const int am = (c * TT + t) % 3;
-          mma_tf32(tmem_d + am * C, ah, bh, idesc, (uint32_t)(c | (t >= 3)));   // first touch overwrites
-          mma_tf32(tmem_d + 3 * C, ah, bl, idesc, (uint32_t)(c | t));
+          const int am = unit % 3;
+          mma_tf32(tmem_d + am * C, ah, bh, idesc, (uint32_t)(unit >= 3));   // first touch overwrites
+          mma_tf32(tmem_d + 3 * C, ah, bl, idesc, (uint32_t)(unit > 0));
           mma_tf32(tmem_d + 3 * C, al, bh, idesc, 1);
         }
         mma_commit(&bar_empty[s]);   // frees the stage when these MMAs have read it
@@ -282,7 +289,7 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv15_tc(cons
     // ---- activation tile: row p <-> (batch row, position - 7), transformed, split into tf32 hi / lo.
     //      One item = 4 channels of one row = one 16-byte core-matrix row: conflict-free vector stores,
     //      global loads coalesced along the row index; 4 items (16-32 loads) in flight per thread.
-    constexpr int NIT = (C / 4) * kRowsA, GI = 2 * kRowsA;   // items, items per group
+    constexpr int NIT = (C / 4) * ROWS, GI = 2 * ROWS;   // items, items per group
     constexpr int UN = 4;
     const int tin = J.tin;
     const bool affine = tin < 0 && J.x2 != nullptr;
@@ -293,11 +300,11 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv15_tc(cons
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int idx = base + u * NLD;
-        const int kc = idx / kRowsA, p = idx - kc * kRowsA;
+        const int kc = idx / ROWS, p = idx - kc * ROWS;
         kcs[u] = kc;
         int bb, pos; bool ok;
-        if (packed) { const int sgi = p / tl.seg; bb = b0 + sgi; pos = p - sgi * tl.seg - 7; ok = sgi < tl.nseg && bb < P.B; }
-        else { bb = b0; pos = l0 - 7 + p; ok = p < 142; }
+        if (packed) { const int sgi = p / tl.seg; bb = b0 + sgi; pos = p - sgi * tl.seg - HALO; ok = sgi < tl.nseg && bb < P.B; }
+        else { bb = b0; pos = l0 - HALO + p; ok = p < 128 + KW - 1; }
         ok = ok && idx < NIT && pos >= 0 && pos < L;
         const long long off = (long long)(4 * kc) * L + pos;
         const float* xr = J.x + (long long)bb * J.xbs + off;
@@ -418,27 +425,33 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv15_tc(cons
   TC_MARK(6);
 }
 
-template <int C>
-static size_t tc_smem_bytes() { return TcCfg<C>::smem; }
-
 static inline bool tc_supported(int C) { return C == 32 || C == 64 || C == 128; }
 
-static int launch_conv15_tc(TcBatch& b, cudaStream_t st) {
+template <int C, int KW>
+static void launch_conv_tc_t(const TcBatch& b, dim3 grid, cudaStream_t st, const char* name) {
+  const size_t smem = TcCfg<C, KW>::smem;
+  static bool prepared = false;
+  if (!prepared) { cudaFuncSetAttribute(k_conv_tc<C, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); prepared = true; }
+  prof_before(name, "", st);
+  k_conv_tc<C, KW><<<grid, dim3(kTcThreads), smem, st>>>(b);
+  prof_after(st);
+}
+
+static int launch_conv_tc(TcBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
   int tiles = 0;
-  for (int i = 0; i < b.n; ++i) { const int t = TcTiling(b.j[i].L).tiles(b.B); tiles = t > tiles ? t : tiles; }
+  for (int i = 0; i < b.n; ++i) { const int t = TcTiling(b.j[i].L, b.KW).tiles(b.B); tiles = t > tiles ? t : tiles; }
   dim3 grid(tiles, 1, b.n);
-#define GNAS_TC_CASE(c)                                                                                   \
-  if (b.C == c) {                                                                                         \
-    const size_t smem = tc_smem_bytes<c>();                                                               \
-    static bool prepared = false;                                                                         \
-    if (!prepared) { cudaFuncSetAttribute(k_conv15_tc<c>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); prepared = true; } \
-    prof_before("k_conv15_tc<" #c ">", "", st);                                                           \
-    k_conv15_tc<c><<<grid, dim3(kTcThreads), smem, st>>>(b);                                              \
-    prof_after(st);                                                                                       \
-  } else
-  GNAS_TC_CASE(32) GNAS_TC_CASE(64) GNAS_TC_CASE(128) { set_error("conv15_tc: unsupported channel count"); return GNAS_ERR_UNSUPPORTED; }
-#undef GNAS_TC_CASE
+  const int key = b.C * 100 + b.KW;
+  switch (key) {
+    case 3215: launch_conv_tc_t<32, 15>(b, grid, st, "k_conv_tc<32,15>"); break;
+    case 6415: launch_conv_tc_t<64, 15>(b, grid, st, "k_conv_tc<64,15>"); break;
+    case 12815: launch_conv_tc_t<128, 15>(b, grid, st, "k_conv_tc<128,15>"); break;
+    case 3201: launch_conv_tc_t<32, 1>(b, grid, st, "k_conv_tc<32,1>"); break;
+    case 6401: launch_conv_tc_t<64, 1>(b, grid, st, "k_conv_tc<64,1>"); break;
+    case 12801: launch_conv_tc_t<128, 1>(b, grid, st, "k_conv_tc<128,1>"); break;
+    default: set_error("conv_tc: unsupported (channels, taps)"); return GNAS_ERR_UNSUPPORTED;
+  }
   b.n = 0;
   return 0;
 }

@@ -14,7 +14,7 @@ using namespace gnas;
 
 int main(int argc, char** argv) {
   const int C = argc > 1 ? atoi(argv[1]) : 64, L = argc > 2 ? atoi(argv[2]) : 125, B = argc > 3 ? atoi(argv[3]) : 64;
-  const int jobs = argc > 4 ? atoi(argv[4]) : 1, mode = argc > 5 ? atoi(argv[5]) : 0;   // mode 0 fwd, 1 dx (BNRELU_STORE)
+  const int jobs = argc > 4 ? atoi(argv[4]) : 1, mode = argc > 5 ? atoi(argv[5]) : 0, KW = argc > 6 ? atoi(argv[6]) : 15;   // mode 0 fwd, 1 dx (BNRELU_STORE)
   const size_t n = (size_t)B * C * L;
   float *x, *x2, *z, *w, *stat, *mref; double* acc;
   cudaMalloc(&x, n * 4 * jobs); cudaMalloc(&x2, n * 4 * jobs); cudaMalloc(&z, n * 4 * jobs); cudaMalloc(&mref, n * 4 * jobs);
@@ -25,7 +25,7 @@ int main(int argc, char** argv) {
   cudaMemcpy(mref, h.data(), n * 4 * jobs, cudaMemcpyHostToDevice);
   cudaMemcpy(w, h.data(), (size_t)2 * C * C * 15 * 4 < n * 4 * jobs ? (size_t)2 * C * C * 15 * 4 : n * 4 * jobs, cudaMemcpyHostToDevice);
   cudaMemset(stat, 0, 3 * C * 4); cudaMemset(acc, 0, 2 * C * 8);
-  tc::TcBatch b; b.B = B; b.C = C;
+  tc::TcBatch b; b.B = B; b.C = C; b.KW = KW;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int reps = 20;
   float ms = 0;
@@ -36,14 +36,15 @@ int main(int argc, char** argv) {
       tc::TcJob& t = b.j[i];
       t.x = x + i * n; t.xbs = (long long)C * L; t.x2 = mode ? x2 + i * n : nullptr; t.x2bs = (long long)C * L; t.in_stat = stat; t.w = w;
       t.z = z + i * n; t.zbs = (long long)C * L; t.acc = acc; t.mref = mode ? mref + i * n : nullptr; t.mrbs = (long long)C * L; t.mstat = stat;
-      t.L = L; t.tin = mode ? -1 : T_BN_RELU; t.omode = mode ? O_BNRELU_STORE : O_STORE;
+      t.L = L; t.tin = mode ? -1 : (KW == 1 ? T_NONE : T_BN_RELU); t.omode = mode ? (KW == 1 ? O_STORE : O_BNRELU_STORE) : O_STORE;
+      if (mode && KW == 1) { t.acc = nullptr; t.mref = nullptr; }
     }
-    tc::launch_conv15_tc(b, 0);
+    tc::launch_conv_tc(b, 0);
   }
   cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
   cudaError_t err = cudaGetLastError();
-  printf("C=%d L=%d B=%d jobs=%d mode=%d: %.1f us/launch (%s) tiles=%d\n", C, L, B, jobs, mode, 1e3 * ms / reps, cudaGetErrorString(err),
-         tc::TcTiling(L).tiles(B) * jobs);
+  printf("C=%d L=%d B=%d jobs=%d mode=%d KW=%d: %.1f us/launch (%s) tiles=%d\n", C, L, B, jobs, mode, KW, 1e3 * ms / reps, cudaGetErrorString(err),
+         tc::TcTiling(L, KW).tiles(B) * jobs);
 #ifdef GNAS_TC_MARKS
   long long m[64];
   cudaMemcpyFromSymbol(m, tc::g_tc_marks, sizeof(m));

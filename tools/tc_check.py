@@ -19,14 +19,17 @@ def shapes(module, prefix):
 
 
 cases = [(2, 32, 125, 1), (3, 32, 250, 1), (2, 64, 125, 1), (5, 64, 42, 1), (2, 128, 200, 1), (1, 128, 200, 1), (3, 128, 42, 1), (4, 128, 42, 1), (7, 32, 20, 1), (4, 64, 300, 1)]
-sw = [False] * 8 + [True]
-for B, C, L, S in cases:
+ALL = [True] * 9
+PW = [False, False, False, False, True, True, True, True, False]
+cases = [(c + ([False] * 8 + [True],)) for c in cases] + [(2, 32, 250, 1, PW), (2, 64, 125, 1, PW), (3, 128, 42, 1, PW), (5, 128, 42, 3, ALL),
+                                                        (2, 64, 125, 2, ALL), (3, 32, 250, 1, ALL), (2, 128, 130, 1, PW)]
+for B, C, L, S, sw in cases:
     torch.manual_seed(1)
     m = G.MixedOp(C, S, sw, 0.0)
     P = O.synthetic_params(shapes(m, "cell_ops.0."), 5)
     m.load_state_dict({k[len("cell_ops.0."):]: v for k, v in P.items()})
     m.to("cuda").train()
-    x0, w0 = torch.randn(B, C, L), torch.ones(1)
+    x0, w0 = torch.randn(B, C, L), torch.softmax(torch.randn(sum(sw)), 0)
     x = x0.clone().cuda().requires_grad_(True); w = w0.clone().cuda().requires_grad_(True)
     y = m(x, w)
     gy = torch.randn(y.shape)
@@ -35,9 +38,10 @@ for B, C, L, S in cases:
     xo, wo = x0.double().requires_grad_(True), w0.double().requires_grad_(True)
     yo = O.mixed_op(xo, wo, sw, S, Q, "cell_ops.0", True, O.Recorder(), 0.0, None)
     (yo * gy.double()).sum().backward()
-    line = [f"B{B} C{C} L{L} S{S}: y {relerr(y, yo):.2e} dx {relerr(x.grad, xo.grad):.2e} dw {relerr(w.grad, wo.grad):.2e}"]
-    for n, p in m.named_parameters():
-        line.append(f"{n.split('.')[-2]} {relerr(p.grad, Q['cell_ops.0.' + n].grad):.2e}")
+    line = [f"B{B} C{C} L{L} S{S} ops{sum(sw)}: y {relerr(y, yo):.2e} dx {relerr(x.grad, xo.grad):.2e} dw {relerr(w.grad, wo.grad):.2e}"]
+    errs = {n: relerr(p.grad, Q['cell_ops.0.' + n].grad) for n, p in m.named_parameters()}
+    worst = max(errs, key=errs.get)
+    line.append(f"worst dW {errs[worst]:.2e} ({worst})")
     print(" | ".join(line), flush=True)
     if os.environ.get("TC_KNIFE"):
         import torch.nn.functional as F
