@@ -2,9 +2,6 @@
 // Replaces darts_tools/model_discCNN.py:46-201 (MixedOp, CNN_Cell_search) and the
 // operator zoo generalNAS_tools/operations_14_9.py behind include/gnas.h.
 #include "launch.cuh"
-#ifndef GNAS_TC_DEFAULT
-#define GNAS_TC_DEFAULT 1
-#endif
 #include "conv15_tc.cuh"
 #include <cstdlib>
 #include "../../include/gnas.h"
@@ -55,16 +52,7 @@ struct CellPlan {
 
 inline long long al4(long long x) { return (x + 3) / 4 * 4; }
 
-// tcgen05 path for the stride-1 conv_15 convolutions (conv15_tc.cuh); GNAS_TC=0 selects the SIMT kernels
-inline bool tc_enabled() {
-#ifdef GNAS_EMUL
-  return false;
-#else
-  static int v = -1;
-  if (v < 0) { const char* s = getenv("GNAS_TC"); v = s ? atoi(s) : GNAS_TC_DEFAULT; }
-  return v != 0;
-#endif
-}
+// tcgen05 path for the stride-1 conv_15 / pointwise convolutions (conv15_tc.cuh); GNAS_TC=0 selects the SIMT kernels
 inline bool tc_on(int C, int stride) {
 #ifdef GNAS_EMUL
   (void)C; (void)stride; return false;

@@ -12,6 +12,8 @@
 // Backward: staged launches per (time step, node) -- elementwise/BN kernel + split-K GEMM against
 // Ws[i]^T -- and, off the critical path, one batched GEMM pass for dW0 / dWs over all time steps.
 #include "common.cuh"
+#include "tc_common.cuh"
+#include "rhn_wgrad_tc.cuh"
 #include "../../include/gnas.h"
 
 namespace gnas {
@@ -954,6 +956,15 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
   GNAS_LAUNCH(k_rhn_untranspose, dim3(ewb((long long)T * B * H)), dim3(256), 0, st, (const float*)(scratch + p.dxT), dx, T, B, BP, H);
   GNAS_LAUNCH(k_rhn_untranspose, dim3(ewb((long long)B * H)), dim3(256), 0, st, (const float*)dhbuf[T & 1], dh0, 1, B, BP, H);
   GNAS_LAUNCH(k_rhn_dprobs, dim3(1), dim3(256), 0, st, (const double*)(scratch + p.dpacc), dprobs, 36 * d->n_prims, tb);
+#ifndef GNAS_EMUL
+  if (need_wgrad && tc_enabled() && tc::rhn_wgrad_tc_supported(B, BP, H)) {
+    tc::RhnWgTc w;
+    w.T = T; w.B = B; w.BP = BP; w.H = H;
+    w.ST = ws + p.ST; w.CHT = ws + p.CHT; w.C0T = ws + p.C0T; w.HT = ws + p.HT; w.h0T = ws + p.h0T;
+    w.xmT = ws + p.xmT; w.hmT = ws + p.hmT; w.dW0 = dW0; w.dWs = dWs;
+    tc::launch_rhn_wgrad_tc(w, st);
+  } else
+#endif
   if (need_wgrad) {
     RhnWg w;
     w.T = T; w.B = B; w.BP = BP; w.H = H;

@@ -69,3 +69,43 @@ def test_rhn_eval_mode(backend, monkeypatch):
                         None, None, training=False)
     assert relerr(y, yo) < TOL_OUT
     assert int(m.bn.num_batches_tracked) == 0
+
+
+@pytest.mark.parametrize("nhid,B,T", [(128, 32, 3), (128, 64, 2)])
+def test_rhn_wide_hidden_matches_oracle(backend, monkeypatch, nhid, B, T):
+    """Hidden sizes that are multiples of 128 with batches that are multiples of 32 take the tcgen05 weight-gradient
+    kernel on the GPU (rhn_wgrad_tc.cuh); the fp64 oracle (pinned to the reference by tests/golden/rhn.pt) is the
+    checker."""
+    if backend != "cuda" and B > 32:
+        pytest.skip("emulator: one wide case is enough")
+    torch.manual_seed(5)
+    switch = [[True] * 5 for _ in range(36)]
+    m = DARTSCellSearch(nhid, nhid, 0.25, 0.25, switch)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.uniform_(-0.08, 0.08)
+    m.weights = torch.nn.Parameter(1e-1 * torch.randn(36, 5))
+    m.to(backend).train()
+    xm = (torch.rand(B, nhid) < 0.75).float() / 0.75
+    hm = (torch.rand(B, nhid) < 0.75).float() / 0.75
+    masks = [xm, hm]
+    monkeypatch.setattr(R, "mask2d", lambda B_, D, keep, dev: masks.pop(0).to(dev))
+    x0, h00, gy = torch.randn(T, B, nhid), 0.1 * torch.randn(B, nhid), torch.randn(T, B, nhid)
+    x, h0 = leaf(x0, backend), leaf(h00, backend)
+    y, _ = m(x, h0[None])
+    (y * gy.to(backend)).sum().backward()
+    P = {("rnns.0." + k): v.detach().double().cpu().requires_grad_(True) for k, v in m.state_dict().items()
+         if v.is_floating_point() and "running" not in k}
+    P.update({"rnns.0.bn.running_mean": torch.zeros(nhid, dtype=torch.float64),
+              "rnns.0.bn.running_var": torch.ones(nhid, dtype=torch.float64)})
+    al = m.weights.detach().double().cpu().requires_grad_(True)
+    xo, ho = x0.double().requires_grad_(True), h00.double().requires_grad_(True)
+    yo, _ = O.rhn_layer(xo, ho, P, "rnns.0", switch, al, xm.double(), hm.double(), True, O.Recorder())
+    (yo * gy.double()).sum().backward()
+    assert relerr(y, yo) < TOL_OUT
+    assert relerr(x.grad, xo.grad) < TOL_GRAD
+    assert relerr(h0.grad, ho.grad) < TOL_GRAD
+    assert relerr(m.weights.grad, al.grad) < TOL_GRAD
+    assert relerr(m._W0.grad, P["rnns.0._W0"].grad) < TOL_GRAD
+    for i, w in enumerate(m._Ws):
+        assert relerr(w.grad, P[f"rnns.0._Ws.{i}"].grad) < TOL_GRAD, i
