@@ -3,6 +3,7 @@
 // operator zoo generalNAS_tools/operations_14_9.py behind include/gnas.h.
 #include "launch.cuh"
 #include "conv15_tc.cuh"
+#include "wgrad_tc.cuh"
 #include <cstdlib>
 #include "../../include/gnas.h"
 
@@ -61,10 +62,10 @@ inline bool tc_on(int C, int stride) {
 #endif
 }
 // debugging aid: GNAS_TC_PART bit 0 = conv_15 forward, bit 1 / 2 = data gradient of its second / first conv,
-// bit 3 = pointwise convs (forward and data gradient)
+// bit 3 = pointwise convs (forward and data gradient), bit 4 = pointwise weight gradient
 inline bool tc_part(int bit) {
   static int v = -1;
-  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 15; }
+  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 31; }
   return (v >> bit) & 1;
 }
 #ifndef GNAS_EMUL
@@ -603,6 +604,12 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     DxBatch xb; xb.n = 0; xb.B = B; xb.Cin = C; xb.pad = 0;
     WgBatch gb; gb.n = 0; gb.B = B; gb.Cout = C;
     auto pw_dx = [&](DxBatch& b) { return tc_pw_on(C) ? launch_conv_dx_tc(b, 1, c.st) : launch_dense_dx(1, 1, b, c.st); };
+    auto pw_wg = [&](WgBatch& b) {
+#ifndef GNAS_EMUL
+      if (tc_on(C, 1) && tc_part(4) && tc::pw_wgrad_tc_supported(b)) return tc::launch_pw_wgrad_tc(b, c.st);
+#endif
+      return launch_pw_wgrad(1, b, c.st);
+    };
     // -- strided skip (FactorizedReduce): dx + dW
     if (S > 1) {
       for (int i = 0; i < n2; ++i) {
@@ -642,11 +649,11 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
           w.r = c.T(e, dwk[v], sep ? 2 : 0); w.rbs = obs; w.r_stat = nullptr; w.dw = c.dW(e, dwk[v], sep ? 3 : 1);
           w.Cin = C; w.Lo = Lo; w.Lin = Lo; w.tin = T_NONE;
         }
-        if (xb.n == kMaxDense) { c.rc |= pw_dx(xb); c.rc |= launch_pw_wgrad(1, gb, c.st); }
+        if (xb.n == kMaxDense) { c.rc |= pw_dx(xb); c.rc |= pw_wg(gb); }
       }
     }
     c.rc |= pw_dx(xb);
-    c.rc |= launch_pw_wgrad(1, gb, c.st);
+    c.rc |= pw_wg(gb);
     // -- depthwise: sep stage 2 (-> dyh1 + inner BN sums), dil (-> dX)
     for (int v = 0; v < 4; ++v) {
       const bool sep = v < 2;
@@ -720,7 +727,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
       }
     }
     c.rc |= pw_dx(xb);
-    c.rc |= launch_pw_wgrad(1, gb, c.st);
+    c.rc |= pw_wg(gb);
     for (int v = 0; v < 2; ++v) {
       DwBwdBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = dwP[v];
       for (int i = 0; i < n2; ++i) {

@@ -1,0 +1,224 @@
+// Pointwise (1x1) conv weight gradients on the 5th-generation tensor cores (3xTF32, fp32 accumulate in TMEM):
+//   dW[co][ci] += sum_{b,l} dz[b][co][l] * u[b][ci][l],   dz = A*g + Bz*z + D  (the BN backward folded into the load)
+// for the pointwise convs of sep_conv / dil_conv (operations_14_9.py:36-64, backward).  Both operands are K-major as
+// they lie in memory (positions contiguous).  128 / C jobs (edges x candidates of one cell node) are stacked along
+// M and N so that one 128 x 128 x 8 MMA serves all of them; the epilogue keeps the diagonal C x C blocks.
+// The kernel is loader-bound (three activation tensors are read once), not MMA-bound.
+#pragma once
+#include "tc_common.cuh"
+#include "cnn_bwd.cuh"
+
+#ifndef GNAS_EMUL
+namespace gnas {
+namespace tc {
+
+struct WgTcBatch { int n, B, rows_per_cta; WgJob j[kMaxDense]; };
+
+constexpr int kPwStages = 3;
+constexpr int kPwOp = 8 * 128 * 4;                 // floats of one operand half: [8 k-chunks][128 rows][4]
+constexpr int kPwStage = 4 * kPwOp;                // A_hi | A_lo | B_hi | B_lo
+constexpr int kPwLoaders = kTcThreads - 32;        // warps 1..7
+constexpr size_t kPwSmem = sizeof(float) * ((size_t)kPwStage * kPwStages + 3 * 128) + 128;
+
+template <int C>
+__global__ void __launch_bounds__(kTcThreads, 1) k_pw_wgrad_tc(const __grid_constant__ WgTcBatch P) {
+  constexpr int NJ = 128 / C;                               // jobs stacked along M and N
+  const int j0 = blockIdx.y * NJ;
+  const int L = P.j[j0].Lo;
+  const int spr = (L + 31) / 32;                            // stages per batch row
+  const int bs = blockIdx.x * P.rows_per_cta, be = min(P.B, bs + P.rows_per_cta);
+  if (bs >= be) return;
+  const int nstage = (be - bs) * spr;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  extern __shared__ __align__(128) unsigned char pw_smem_raw[];
+  float* sm = reinterpret_cast<float*>(pw_smem_raw);
+  float* coef = sm + (size_t)kPwStage * kPwStages;          // [3][128]: A | Bz | D per stacked output channel
+  __shared__ __align__(8) uint64_t bar_full[kPwStages], bar_empty[kPwStages], bar_done;
+  __shared__ uint32_t tmem_base_s;
+  constexpr uint32_t LBO = 128 * 16, SBO = 128;
+  constexpr int TM_COLS = 512;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+#pragma unroll
+    for (int i = 0; i < kPwStages; ++i) { mbar_init(&bar_full[i], kPwLoaders); mbar_init(&bar_empty[i], 1); }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 3 * 128; i += kTcThreads) {
+    const int which = i >> 7, r = i & 127, jl = r / C, ch = r - jl * C;
+    float v = which == 0 ? 1.f : 0.f;
+    if (j0 + jl < P.n && P.j[j0 + jl].z != nullptr) v = P.j[j0 + jl].coef[which * C + ch];
+    coef[i] = v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    // ---- MMA issuer (whole warp loops, one elected lane issues)
+    const uint32_t idesc = make_idesc(128);
+    const uint64_t d0 = make_desc(smem_u32(sm), LBO, SBO);
+    int cnt = 0;
+    for (int st = 0; st < nstage; ++st) {
+      const int s = st % kPwStages;
+      mbar_wait(&bar_full[s], (st / kPwStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t base = d0 + (uint64_t)(((uint32_t)s * kPwStage * 4) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t koff = (uint64_t)((ks * 2 * LBO) >> 4);
+          const uint64_t ah = base + koff, al = ah + (uint64_t)((kPwOp * 4) >> 4);
+          const uint64_t bh = base + koff + (uint64_t)((2 * kPwOp * 4) >> 4), bl = bh + (uint64_t)((kPwOp * 4) >> 4);
+          const int unit = cnt + ks;
+          mma_tf32(tmem_d + (unit % 3) * 128, ah, bh, idesc, (uint32_t)(unit >= 3));   // hi*hi: accumulators 0..2 in turn
+          mma_tf32(tmem_d + 3 * 128, ah, bl, idesc, (uint32_t)(unit > 0));              // cross terms: accumulator 3
+          mma_tf32(tmem_d + 3 * 128, al, bh, idesc, 1);
+        }
+        mma_commit(&bar_empty[s]);
+      }
+      cnt += 4;
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(&bar_done);
+    __syncwarp();
+  } else {
+    // ---- loaders: 4 consecutive positions of one channel -> (affine) -> tf32 hi / lo -> one 16-byte core-matrix row
+    const int lt = tid - 32;
+    constexpr int NIT = 2048, PER = (NIT + kPwLoaders - 1) / kPwLoaders;   // items per stage, per thread
+    for (int st = 0; st < nstage; ++st) {
+      const int s = st % kPwStages;
+      if (st >= kPwStages) mbar_wait(&bar_empty[s], ((st / kPwStages) - 1) & 1);
+      const int b = bs + st / spr, p0 = (st % spr) * 32;
+      float* stage = sm + (size_t)s * kPwStage;
+      float xv[PER][4], yv[PER][4];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int idx = lt + i * kPwLoaders;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { xv[i][e] = 0.f; yv[i][e] = 0.f; }
+        if (idx >= NIT) continue;
+        const int op = idx >> 10, q = idx & 1023, rb = q >> 5, w = q & 31;
+        const int r = (rb & 7) * 16 + (w & 15), jc = 2 * (rb >> 3) + (w >> 4);
+        const int jl = r / C, ch = r - jl * C;
+        if (j0 + jl >= P.n) continue;
+        const WgJob& J = P.j[j0 + jl];
+        const int pos = p0 + 4 * jc;
+        if (op == 0) {
+          const float* gp = J.g + (long long)b * J.gbs + (long long)ch * L + pos;
+          const float* zp = J.z ? J.z + (long long)b * J.zbs + (long long)ch * L + pos : nullptr;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (pos + e < L) { xv[i][e] = gp[e]; if (zp) yv[i][e] = zp[e]; }
+        } else {
+          const float* rp = J.r + (long long)b * J.rbs + (long long)ch * L + pos;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (pos + e < L) xv[i][e] = rp[e];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int idx = lt + i * kPwLoaders;
+        if (idx >= NIT) continue;
+        const int op = idx >> 10, q = idx & 1023, rb = q >> 5, w = q & 31;
+        const int r = (rb & 7) * 16 + (w & 15), jc = 2 * (rb >> 3) + (w >> 4);
+        const int pos = p0 + 4 * jc;
+        float a[4], h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          a[e] = xv[i][e];
+          if (op == 0) a[e] = (pos + e < L) ? fmaf(coef[r], xv[i][e], fmaf(coef[128 + r], yv[i][e], coef[256 + r])) : 0.f;
+          h[e] = __uint_as_float(to_tf32(a[e]));
+          l[e] = __uint_as_float(to_tf32(a[e] - h[e]));
+        }
+        float* dst = stage + (size_t)op * 2 * kPwOp + ((size_t)jc * 128 + r) * 4;
+        *reinterpret_cast<float4*>(dst) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(dst + kPwOp) = make_float4(l[0], l[1], l[2], l[3]);
+      }
+      fence_async_smem();
+      mbar_arrive(&bar_full[s]);
+    }
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM -> registers -> red.add of the diagonal C x C blocks into the gradients
+  mbar_wait(&bar_done, 0);
+  tc_fence_after();
+  {
+    const int q4 = warp & 3;
+    const int row = 32 * q4 + lane;
+    const int jl = row / C, co = row - jl * C;                // jl is uniform per warp (C >= 32)
+    constexpr int NB = C / 32;                                // 32-column blocks of the diagonal block
+    if (j0 + jl < P.n) {
+      float* orow = P.j[j0 + jl].dw + (size_t)co * C;
+      for (int blk = (warp >> 2); blk < NB; blk += 2) {
+        const int c0 = jl * C + blk * 32;
+        float v[32];
+        const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)c0;
+        tmem_ld32(taddr, v);
+#pragma unroll
+        for (int a = 1; a < 4; ++a) {
+          float t[32];
+          tmem_ld32(taddr + a * 128, t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) red_add_v4(orow + blk * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TM_COLS) : "memory");
+  }
+}
+
+template <int C>
+static void launch_pw_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* name) {
+  static bool prepared = false;
+  if (!prepared) { cudaFuncSetAttribute(k_pw_wgrad_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPwSmem); prepared = true; }
+  const int groups = cdiv(b.n, 128 / C);
+  int ksplit = cdiv(2 * 148, groups);
+  ksplit = ksplit > b.B ? b.B : (ksplit < 1 ? 1 : ksplit);
+  b.rows_per_cta = cdiv(b.B, ksplit);
+  prof_before(name, "", st);
+  k_pw_wgrad_tc<C><<<dim3(cdiv(b.B, b.rows_per_cta), groups), dim3(kTcThreads), kPwSmem, st>>>(b);
+  prof_after(st);
+}
+
+// jobs must share (Cout = Cin = C, stride 1, no input transform, Lo = Lin)
+static inline bool pw_wgrad_tc_supported(const WgBatch& b) {
+  if (!(b.Cout == 32 || b.Cout == 64 || b.Cout == 128)) return false;
+  for (int i = 0; i < b.n; ++i) {
+    const WgJob& j = b.j[i];
+    if (j.Cin != b.Cout || j.tin != T_NONE || j.Lo != j.Lin || j.Lo != b.j[0].Lo) return false;
+  }
+  return true;
+}
+
+static int launch_pw_wgrad_tc(WgBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  WgTcBatch t; t.n = b.n; t.B = b.B;
+  for (int i = 0; i < b.n; ++i) t.j[i] = b.j[i];
+  switch (b.Cout) {
+    case 32: launch_pw_wgrad_tc_t<32>(t, st, "k_pw_wgrad_tc<32>"); break;
+    case 64: launch_pw_wgrad_tc_t<64>(t, st, "k_pw_wgrad_tc<64>"); break;
+    default: launch_pw_wgrad_tc_t<128>(t, st, "k_pw_wgrad_tc<128>"); break;
+  }
+  b.n = 0;
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace gnas
+#endif  // !GNAS_EMUL
