@@ -62,10 +62,11 @@ inline bool tc_on(int C, int stride) {
 #endif
 }
 // debugging aid: GNAS_TC_PART bit 0 = conv_15 forward, bit 1 / 2 = data gradient of its second / first conv,
-// bit 3 = pointwise convs (forward and data gradient), bit 4 = pointwise weight gradient
+// bit 3 = pointwise convs (forward and data gradient), bit 4 = pointwise weight gradient,
+// bit 5 = conv_15 weight gradient
 inline bool tc_part(int bit) {
   static int v = -1;
-  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 31; }
+  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 63; }
   return (v >> bit) & 1;
 }
 #ifndef GNAS_EMUL
@@ -604,6 +605,12 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     DxBatch xb; xb.n = 0; xb.B = B; xb.Cin = C; xb.pad = 0;
     WgBatch gb; gb.n = 0; gb.B = B; gb.Cout = C;
     auto pw_dx = [&](DxBatch& b) { return tc_pw_on(C) ? launch_conv_dx_tc(b, 1, c.st) : launch_dense_dx(1, 1, b, c.st); };
+    auto conv_wg = [&](WgBatch& b, int stride) {
+#ifndef GNAS_EMUL
+      if (tc_on(C, stride) && tc_part(5) && tc::conv_wgrad_tc_supported(b)) return tc::launch_conv_wgrad_tc(b, c.st);
+#endif
+      return launch_conv_wgrad(15, stride, 7, b, c.st);
+    };
     auto pw_wg = [&](WgBatch& b) {
 #ifndef GNAS_EMUL
       if (tc_on(C, 1) && tc_part(4) && tc::pw_wgrad_tc_supported(b)) return tc::launch_pw_wgrad_tc(b, c.st);
@@ -695,7 +702,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
       }
     }
     c.rc |= tc_dx_on(C, 1, 1) ? launch_conv_dx_tc(xb, 15, c.st) : launch_dense_dx(15, 1, xb, c.st);
-    c.rc |= launch_conv_wgrad(15, 1, 7, gb, c.st);
+    c.rc |= conv_wg(gb, 1);
     // -- inner BN coefficients (w = 1)
     {
       int sl[16], wi[16], n = 0;
@@ -760,7 +767,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
       }
     }
     c.rc |= tc_dx_on(C, S, 0) ? launch_conv_dx_tc(xb, 15, c.st) : launch_dense_dx(15, S, xb, c.st);
-    c.rc |= launch_conv_wgrad(15, S, 7, gb, c.st);
+    c.rc |= conv_wg(gb, S);
   }
 }
 

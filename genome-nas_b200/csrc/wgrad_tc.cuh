@@ -219,6 +219,244 @@ static int launch_pw_wgrad_tc(WgBatch& b, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------ conv_15 weight gradient (stride 1)
+//   dW[co][ci][t] += sum_{b,l} dz[b][co][l] * R[b][ci][l + t - 7],    R = ReLU(x) or ReLU(BN(z1))
+// Positions are the reduction (K) dimension, so a tap is a shift along K; K-major operands only shift in whole
+// 16-byte chunks (4 positions).  The other three shifts are put into the rows: the A tile holds RA = 128 / C copies
+// of dz shifted by sa = 0..RA-1 positions, the B tile RB = 4 / RA copies of R shifted by RA * sb, and the MMA for
+// tap group a reads B four positions (one chunk) further on:  t = sa + RA * sb + 4 * a  (t = 15 is discarded).
+// C = 128 has RB = 4 row blocks of 128: one CTA per block (blockIdx.z).
+template <int C> struct CwCfg {
+  static constexpr int RA = 128 / C, RB = 4 / RA;
+  static constexpr int NB = C == 32 ? 32 : 128;             // B rows per CTA (= MMA N)
+  static constexpr int NZ = C == 128 ? 4 : 1;               // CTAs along the sb dimension
+  static constexpr int BCH = 11;                            // B chunks per stage: 8 + 3 (tap groups)
+  static constexpr int A_OP = 8 * 128 * 4, B_OP = BCH * NB * 4;
+  static constexpr int STAGE = 2 * A_OP + 2 * B_OP;         // floats
+  static constexpr int NST = C == 32 ? 3 : 2;
+  static constexpr size_t smem = sizeof(float) * ((size_t)STAGE * NST + 3 * 128 + 2 * 128) + 128;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_constant__ WgTcBatch P) {
+  using Cfg = CwCfg<C>;
+  constexpr int RA = Cfg::RA, NB = Cfg::NB, BCH = Cfg::BCH, NST = Cfg::NST, A_OP = Cfg::A_OP, B_OP = Cfg::B_OP, STAGE = Cfg::STAGE;
+  const WgJob& J = P.j[blockIdx.y];
+  const int L = J.Lo;
+  const int spr = (L + 3 + 31) / 32;                        // stages per batch row (rows shifted by up to 3)
+  const int bs = blockIdx.x * P.rows_per_cta, be = min(P.B, bs + P.rows_per_cta);
+  if (bs >= be) return;
+  const int nstage = (be - bs) * spr;
+  const int sb0 = C == 128 ? blockIdx.z : 0;                // first B row block of this CTA
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  extern __shared__ __align__(128) unsigned char cw_smem_raw[];
+  float* sm = reinterpret_cast<float*>(cw_smem_raw);
+  float* coef = sm + (size_t)STAGE * NST;                   // [3][128]: A | Bz | D per A row
+  float* bpar = coef + 3 * 128;                             // [2][128]: mean | rstd per B row
+  __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_done;
+  __shared__ uint32_t tmem_base_s;
+  constexpr uint32_t LBO_A = 128 * 16, LBO_B = NB * 16, SBO = 128;
+  constexpr int TM_COLS = 4 * NB;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+#pragma unroll
+    for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], kPwLoaders); mbar_init(&bar_empty[i], 1); }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 3 * 128; i += kTcThreads) {
+    const int which = i >> 7, ch = (i & 127) % C;
+    coef[i] = J.z != nullptr ? J.coef[which * C + ch] : (which == 0 ? 1.f : 0.f);
+  }
+  for (int i = tid; i < 2 * 128; i += kTcThreads) {
+    const int which = i >> 7, ch = (i & 127) % C;
+    bpar[i] = J.tin == T_BN_RELU ? J.r_stat[which * C + ch] : (which == 0 ? 0.f : 1.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    // ---- MMA issuer
+    const uint32_t idesc = make_idesc(NB);
+    const uint64_t a0 = make_desc(smem_u32(sm), LBO_A, SBO), b0 = make_desc(smem_u32(sm + 2 * A_OP), LBO_B, SBO);
+    for (int st = 0; st < nstage; ++st) {
+      const int s = st % NST;
+      mbar_wait(&bar_full[s], (st / NST) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)(((uint32_t)s * STAGE * 4) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ah = a0 + so + (uint64_t)((ks * 2 * LBO_A) >> 4), al = ah + (uint64_t)((A_OP * 4) >> 4);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const uint64_t bh = b0 + so + (uint64_t)(((ks * 2 + a) * LBO_B) >> 4), bl = bh + (uint64_t)((B_OP * 4) >> 4);
+            const uint32_t acc = tmem_d + a * NB;
+            mma_tf32(acc, ah, bh, idesc, (uint32_t)(st | ks));     // first touch overwrites
+            mma_tf32(acc, ah, bl, idesc, 1);
+            mma_tf32(acc, al, bh, idesc, 1);
+          }
+        }
+        mma_commit(&bar_empty[s]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(&bar_done);
+    __syncwarp();
+  } else {
+    // ---- loaders
+    const int lt = tid - 32;
+    constexpr int NA = 8 * 128, NBI = BCH * NB, NIT = NA + NBI, PER = (NIT + kPwLoaders - 1) / kPwLoaders;
+    const int tin = J.tin;
+    for (int st = 0; st < nstage; ++st) {
+      const int s = st % NST;
+      if (st >= NST) mbar_wait(&bar_empty[s], ((st / NST) - 1) & 1);
+      const int b = bs + st / spr, p0 = (st % spr) * 32;
+      float* stage = sm + (size_t)s * STAGE;
+      const float* gb = J.g + (long long)b * J.gbs;
+      const float* zb = J.z ? J.z + (long long)b * J.zbs : nullptr;
+      const float* rb_ = J.r + (long long)b * J.rbs;
+      float xv[PER][4], yv[PER][4];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int idx = lt + i * kPwLoaders;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { xv[i][e] = 0.f; yv[i][e] = 0.f; }
+        if (idx >= NIT) continue;
+        if (idx < NA) {                       // A: row (sa, co), chunk jc: dz[co][p0 + 4 jc + e - sa]
+          const int rbk = idx >> 5, w = idx & 31;
+          const int r = (rbk & 7) * 16 + (w & 15), jc = 2 * (rbk >> 3) + (w >> 4);
+          const int sa = r / C, ch = r - sa * C;
+          const int pos = p0 + 4 * jc - sa;
+          const float* gp = gb + (long long)ch * L + pos;
+          const float* zp = zb ? zb + (long long)ch * L + pos : nullptr;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (pos + e >= 0 && pos + e < L) { xv[i][e] = gp[e]; if (zp) yv[i][e] = zp[e]; }
+        } else {                              // B: row (sb, ci), chunk jc: R[ci][p0 + 4 jc + e + RA sb - 7]
+          const int q = idx - NA;
+          const int jc = q / NB, r = q - jc * NB;
+          const int sbl = r / C, ch = r - sbl * C;
+          const int pos = p0 + 4 * jc + RA * (sb0 + sbl) - 7;
+          const float* rp = rb_ + (long long)ch * L + pos;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (pos + e >= 0 && pos + e < L) xv[i][e] = rp[e];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int idx = lt + i * kPwLoaders;
+        if (idx >= NIT) continue;
+        float a[4], h[4], l[4];
+        float* dst;
+        if (idx < NA) {
+          const int rbk = idx >> 5, w = idx & 31;
+          const int r = (rbk & 7) * 16 + (w & 15), jc = 2 * (rbk >> 3) + (w >> 4);
+          const int pos = p0 + 4 * jc - r / C;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            a[e] = (pos + e >= 0 && pos + e < L) ? fmaf(coef[r], xv[i][e], fmaf(coef[128 + r], yv[i][e], coef[256 + r])) : 0.f;
+          dst = stage + ((size_t)jc * 128 + r) * 4;
+        } else {
+          const int q = idx - NA;
+          const int jc = q / NB, r = q - jc * NB;
+          const int pos = p0 + 4 * jc + RA * (sb0 + r / C) - 7;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v = xv[i][e];
+            if (tin == T_BN_RELU) v = (v - bpar[r]) * bpar[128 + r];
+            if (tin == T_RELU || tin == T_BN_RELU) v = v > 0.f ? v : 0.f;
+            a[e] = (pos + e >= 0 && pos + e < L) ? v : 0.f;
+          }
+          dst = stage + 2 * A_OP + ((size_t)jc * NB + r) * 4;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { h[e] = __uint_as_float(to_tf32(a[e])); l[e] = __uint_as_float(to_tf32(a[e] - h[e])); }
+        *reinterpret_cast<float4*>(dst) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(dst + (idx < NA ? A_OP : B_OP)) = make_float4(l[0], l[1], l[2], l[3]);
+      }
+      fence_async_smem();
+      mbar_arrive(&bar_full[s]);
+    }
+  }
+  __syncwarp();
+
+  // ---- epilogue: D_a[(sa, co)][(sb, ci)] -> dW[co][ci][sa + RA sb + 4 a]
+  mbar_wait(&bar_done, 0);
+  tc_fence_after();
+  {
+    const int q4 = warp & 3;
+    const int row = 32 * q4 + lane;
+    const int sa = row / C, co = row - sa * C;
+    constexpr int NBLK = NB / 32;
+    float* wrow = J.dw + (size_t)co * C * 15;
+    for (int u = (warp >> 2); u < 4 * NBLK; u += 2) {
+      const int a = u / NBLK, blk = u - a * NBLK;
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(a * NB + blk * 32), v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int col = blk * 32 + i;
+        const int sbl = col / C, ci = col - sbl * C;
+        const int t = sa + RA * (sb0 + sbl) + 4 * a;
+        if (t < 15) atomicAdd(wrow + (size_t)ci * 15 + t, v[i]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TM_COLS) : "memory");
+  }
+}
+
+template <int C>
+static void launch_conv_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* name) {
+  using Cfg = CwCfg<C>;
+  static bool prepared = false;
+  if (!prepared) { cudaFuncSetAttribute(k_conv_wgrad_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem); prepared = true; }
+  const int L = b.j[0].Lo, spr = (L + 3 + 31) / 32;
+  int rows = 10 / spr;                       // ~10 stages (= 40 k-steps) per accumulation chain
+  rows = rows < 1 ? 1 : rows;
+  b.rows_per_cta = rows;
+  prof_before(name, "", st);
+  k_conv_wgrad_tc<C><<<dim3(cdiv(b.B, rows), b.n, Cfg::NZ), dim3(kTcThreads), Cfg::smem, st>>>(b);
+  prof_after(st);
+}
+
+// jobs must share (Cout = Cin = C, stride 1, Lo = Lin)
+static inline bool conv_wgrad_tc_supported(const WgBatch& b) {
+  if (!(b.Cout == 32 || b.Cout == 64 || b.Cout == 128)) return false;
+  for (int i = 0; i < b.n; ++i) {
+    const WgJob& j = b.j[i];
+    if (j.Cin != b.Cout || j.Lo != j.Lin || j.Lo != b.j[0].Lo) return false;
+    if (!(j.tin == T_RELU || j.tin == T_BN_RELU || j.tin == T_NONE)) return false;
+  }
+  return true;
+}
+
+static int launch_conv_wgrad_tc(WgBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  WgTcBatch t; t.n = b.n; t.B = b.B;
+  for (int i = 0; i < b.n; ++i) t.j[i] = b.j[i];
+  switch (b.Cout) {
+    case 32: launch_conv_wgrad_tc_t<32>(t, st, "k_conv_wgrad_tc<32>"); break;
+    case 64: launch_conv_wgrad_tc_t<64>(t, st, "k_conv_wgrad_tc<64>"); break;
+    default: launch_conv_wgrad_tc_t<128>(t, st, "k_conv_wgrad_tc<128>"); break;
+  }
+  b.n = 0;
+  return 0;
+}
+
 }  // namespace tc
 }  // namespace gnas
 #endif  // !GNAS_EMUL
