@@ -546,7 +546,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         else { c.src(e, t.z, t.bs); t.slot = -1; t.mask = c.mask(e); }
       }
     }
-    GNAS_LAUNCH(k_bwd_reduce, dim3(C, cdiv(B, 8)), dim3(kThreads), 0, c.st, rb);
+    GNAS_LAUNCH(k_bwd_reduce, dim3(C, cdiv(B, 8), red_term_chunks(rb.nterms)), dim3(kThreads), 0, c.st, rb);
   }
   auto coef_launch = [&](const int* slots, const int* widx, int n, int s1_slot) {
     if (n == 0) return;
@@ -781,7 +781,7 @@ void preprocess_backward(Ctx& c, float* ds0, float* ds1, int need_wgrad) {
     rb.B = B; rb.C = C; rb.L = Lp; rb.nterms = 1; rb.s1_slot = -1;
     rb.g = c.scratch + c.P.dS[i]; rb.gbs = bs; rb.bacc = reinterpret_cast<double*>(c.scratch + c.P.bacc); rb.dmix = c.dmix();
     rb.t[0].z = c.ws + c.P.pre_z[i]; rb.t[0].bs = bs; rb.t[0].mask = nullptr; rb.t[0].slot = i; rb.t[0].widx = -1;
-    GNAS_LAUNCH(k_bwd_reduce, dim3(C, cdiv(B, 8)), dim3(kThreads), 0, c.st, rb);
+    GNAS_LAUNCH(k_bwd_reduce, dim3(C, cdiv(B, 8), red_term_chunks(rb.nterms)), dim3(kThreads), 0, c.st, rb);
   }
   {
     CoefBatch cb;

@@ -25,54 +25,72 @@ struct RedBatch {
   RedTerm t[kMaxTerms];
 };
 
-// CTA: channel c, 8 batch rows (one per warp).  bacc[slot] = (sum g, sum g*z)
+// CTA: channel c, 8 batch rows (one per warp), kRedTerms terms (blockIdx.z).  bacc[slot] = (sum g, sum g*z).
+// The terms of a chunk are reduced together: g is read once per position and the kRedTerms independent z streams
+// keep that many loads in flight per lane; the term chunks give small-C cells enough CTAs to fill the machine.
+constexpr int kRedTerms = 4;
 static __global__ void __launch_bounds__(kThreads) k_bwd_reduce(const __grid_constant__ RedBatch P) {
   const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y * 8 + warp;
-  __shared__ float red[8];
+  const int t0 = blockIdx.z * kRedTerms;
+  const int nt = P.nterms - t0 < kRedTerms ? P.nterms - t0 : kRedTerms;     // may be <= 0 for the S1-only CTA
+  __shared__ float red[8][kRedTerms + 1];
   const bool ok = b < P.B;
   const float* gr = P.g + (long long)(ok ? b : 0) * P.gbs + (long long)c * P.L;
-  float s1 = 0.f;
-  if (ok) for (int l = lane; l < P.L; l += 32) s1 += gr[l];
-  s1 = warp_sum(s1);
-  if (lane == 0) red[warp] = s1;
-  __syncthreads();
-  double S1 = 0.0;
-  if (threadIdx.x == 0) {
-    for (int w = 0; w < 8; ++w) S1 += (double)red[w];
-    if (P.s1_slot >= 0) atomicAdd(&P.bacc[(long long)P.s1_slot * 2 * P.C + c], S1);
+  const float* zr[kRedTerms]; const float* mr[kRedTerms];
+#pragma unroll
+  for (int k = 0; k < kRedTerms; ++k) {
+    const RedTerm& T = P.t[k < nt ? t0 + k : (t0 < P.nterms ? t0 : 0)];
+    zr[k] = T.z + (long long)(ok ? b : 0) * T.bs + (long long)c * P.L;
+    mr[k] = T.mask ? T.mask + ((long long)(ok ? b : 0) * P.C + c) * P.L : nullptr;
   }
-  for (int t = 0; t < P.nterms; ++t) {
-    const RedTerm& T = P.t[t];
-    float s2 = 0.f;
-    if (ok) {
-      const float* zr = T.z + (long long)b * T.bs + (long long)c * P.L;
-      if (T.mask) {
-        const float* mr = T.mask + ((long long)b * P.C + c) * P.L;
-        _Pragma("unroll 4")
-        for (int l = lane; l < P.L; l += 32) s2 = fmaf(gr[l], zr[l] * mr[l], s2);
-      } else {
-        _Pragma("unroll 4")
-        for (int l = lane; l < P.L; l += 32) s2 = fmaf(gr[l], zr[l], s2);
+  float s1 = 0.f, s2[kRedTerms];
+#pragma unroll
+  for (int k = 0; k < kRedTerms; ++k) s2[k] = 0.f;
+  if (ok && P.nterms > 0) {
+    _Pragma("unroll 2")
+    for (int l = lane; l < P.L; l += 32) {
+      const float gl = gr[l];
+      s1 += gl;
+#pragma unroll
+      for (int k = 0; k < kRedTerms; ++k) {
+        float zv = zr[k][l];
+        if (mr[k]) zv *= mr[k][l];
+        s2[k] = fmaf(gl, zv, s2[k]);
       }
     }
-    s2 = warp_sum(s2);
-    __syncthreads();
-    if (lane == 0) red[warp] = s2;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double S2 = 0.0;
-      for (int w = 0; w < 8; ++w) S2 += (double)red[w];
-      if (T.slot >= 0) {
-        double* a = P.bacc + (long long)T.slot * 2 * P.C;
-        if (P.s1_slot < 0) atomicAdd(&a[c], S1);
-        atomicAdd(&a[P.C + c], S2);
-      } else {
-        atomicAdd(&P.dmix[T.widx], S2);
-      }
+  } else if (ok) {
+    for (int l = lane; l < P.L; l += 32) s1 += gr[l];
+  }
+  s1 = warp_sum(s1);
+#pragma unroll
+  for (int k = 0; k < kRedTerms; ++k) s2[k] = warp_sum(s2[k]);
+  if (lane == 0) {
+    red[warp][kRedTerms] = s1;
+#pragma unroll
+    for (int k = 0; k < kRedTerms; ++k) red[warp][k] = s2[k];
+  }
+  __syncthreads();
+  if (threadIdx.x <= kRedTerms) {
+    const int k = threadIdx.x;
+    double S = 0.0;
+    for (int w = 0; w < 8; ++w) S += (double)red[w][k];
+    if (k == kRedTerms) {
+      if (blockIdx.z == 0 && P.s1_slot >= 0) atomicAdd(&P.bacc[(long long)P.s1_slot * 2 * P.C + c], S);
+    } else if (k < nt) {
+      const RedTerm& T = P.t[t0 + k];
+      if (T.slot >= 0) atomicAdd(&P.bacc[(long long)T.slot * 2 * P.C + P.C + c], S);
+      else atomicAdd(&P.dmix[T.widx], S);
+    }
+    // per-term sum(g) (no shared slot): the value sits in red[..][kRedTerms]
+    if (k < nt && P.s1_slot < 0 && P.t[t0 + k].slot >= 0) {
+      double S1 = 0.0;
+      for (int w = 0; w < 8; ++w) S1 += (double)red[w][kRedTerms];
+      atomicAdd(&P.bacc[(long long)P.t[t0 + k].slot * 2 * P.C + c], S1);
     }
   }
 }
+static inline int red_term_chunks(int nterms) { return nterms > 0 ? (nterms + kRedTerms - 1) / kRedTerms : 1; }
 
 // ------------------------------------------------------------------ coefficients A | Bz | D
 struct CoefBatch {

@@ -81,7 +81,7 @@ extern "C" int gnas_stem_backward(int B, int C0, int L, const float* x, const fl
   rb.g = dout; rb.gbs = bs; rb.bacc = reinterpret_cast<double*>(scratch + p.bacc);
   rb.dmix = reinterpret_cast<double*>(scratch + p.dmix);
   rb.t[0].z = ws + p.z; rb.t[0].bs = bs; rb.t[0].mask = nullptr; rb.t[0].slot = 0; rb.t[0].widx = -1;
-  GNAS_LAUNCH(k_bwd_reduce, dim3(C0, cdiv(B, 8)), dim3(kThreads), 0, st, rb);
+  GNAS_LAUNCH(k_bwd_reduce, dim3(C0, cdiv(B, 8), red_term_chunks(rb.nterms)), dim3(kThreads), 0, st, rb);
   CoefBatch cb;
   cb.bacc = reinterpret_cast<const double*>(scratch + p.bacc); cb.stat = ws + p.stat; cb.coef = scratch + p.coef;
   cb.mixw = nullptr; cb.dmix = reinterpret_cast<double*>(scratch + p.dmix);

@@ -154,10 +154,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pw_wgrad_tc(const __grid_cons
   {
     const int q4 = warp & 3;
     const int row = 32 * q4 + lane;
-    const int jl = row / C, co = row - jl * C;                // jl is uniform per warp (C >= 32)
-    constexpr int NB = C / 32;                                // 32-column blocks of the diagonal block
-    if (j0 + jl < P.n) {
-      float* orow = P.j[j0 + jl].dw + (size_t)co * C;
+    const int jl = row / C, co = row - jl * C;
+    const bool have = j0 + jl < P.n;
+    float* orow = have ? P.j[j0 + jl].dw + (size_t)co * C : nullptr;
+    if constexpr (C >= 32) {
+      constexpr int NB = C / 32;                              // 32-column blocks of the diagonal block (jl is warp-uniform)
       for (int blk = (warp >> 2); blk < NB; blk += 2) {
         const int c0 = jl * C + blk * 32;
         float v[32];
@@ -170,8 +171,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pw_wgrad_tc(const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += t[i];
         }
+        if (have) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) red_add_v4(orow + blk * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int i = 0; i < 32; i += 4) red_add_v4(orow + blk * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+      }
+    } else if (warp < 4) {
+      // several jobs per warp: the diagonal blocks of rows 32 q4 .. 32 q4 + 31 all lie in columns 32 q4 .. 32 q4 + 31
+      float v[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(32 * q4);
+      tmem_ld32(taddr, v);
+#pragma unroll
+      for (int a = 1; a < 4; ++a) {
+        float t[32];
+        tmem_ld32(taddr + a * 128, t);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += t[i];
+      }
+      const int og_mine = (lane - lane % C) / C;
+      float o[C];
+#pragma unroll
+      for (int og = 0; og < 32 / C; ++og)
+        if (og == og_mine) {
+#pragma unroll
+          for (int i = 0; i < C; ++i) o[i] = v[og * C + i];
+        }
+      if (have) {
+#pragma unroll
+        for (int i = 0; i < C; i += 4) red_add_v4(orow + i, o[i], o[i + 1], o[i + 2], o[i + 3]);
       }
     }
   }
@@ -197,8 +224,9 @@ static void launch_pw_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* name
 }
 
 // jobs must share (Cout = Cin = C, stride 1, no input transform, Lo = Lin)
+static inline bool wgrad_tc_channels(int C) { return C == 8 || C == 16 || C == 32 || C == 64 || C == 128; }
 static inline bool pw_wgrad_tc_supported(const WgBatch& b) {
-  if (!(b.Cout == 32 || b.Cout == 64 || b.Cout == 128)) return false;
+  if (!wgrad_tc_channels(b.Cout)) return false;
   for (int i = 0; i < b.n; ++i) {
     const WgJob& j = b.j[i];
     if (j.Cin != b.Cout || j.tin != T_NONE || j.Lo != j.Lin || j.Lo != b.j[0].Lo) return false;
@@ -211,6 +239,8 @@ static int launch_pw_wgrad_tc(WgBatch& b, cudaStream_t st) {
   WgTcBatch t; t.n = b.n; t.B = b.B;
   for (int i = 0; i < b.n; ++i) t.j[i] = b.j[i];
   switch (b.Cout) {
+    case 8: launch_pw_wgrad_tc_t<8>(t, st, "k_pw_wgrad_tc<8>"); break;
+    case 16: launch_pw_wgrad_tc_t<16>(t, st, "k_pw_wgrad_tc<16>"); break;
     case 32: launch_pw_wgrad_tc_t<32>(t, st, "k_pw_wgrad_tc<32>"); break;
     case 64: launch_pw_wgrad_tc_t<64>(t, st, "k_pw_wgrad_tc<64>"); break;
     default: launch_pw_wgrad_tc_t<128>(t, st, "k_pw_wgrad_tc<128>"); break;
@@ -225,25 +255,32 @@ static int launch_pw_wgrad_tc(WgBatch& b, cudaStream_t st) {
 // 16-byte chunks (4 positions).  The other three shifts are put into the rows: the A tile holds RA = 128 / C copies
 // of dz shifted by sa = 0..RA-1 positions, the B tile RB = 4 / RA copies of R shifted by RA * sb, and the MMA for
 // tap group a reads B four positions (one chunk) further on:  t = sa + RA * sb + 4 * a  (t = 15 is discarded).
-// C = 128 has RB = 4 row blocks of 128: one CTA per block (blockIdx.z).
+// C = 128 has RB = 4 row blocks of 128: one CTA per block (blockIdx.z).  C = 16 / 8 carry 8 / 16 sub-shifts in the A
+// rows, so a tap group covers 8 / 16 taps and the groups are 2 / 4 chunks apart.
 template <int C> struct CwCfg {
-  static constexpr int RA = 128 / C, RB = 4 / RA;
-  static constexpr int NB = C == 32 ? 32 : 128;             // B rows per CTA (= MMA N)
+  static constexpr int RA = 128 / C;                        // sub-shifts carried by the A rows
+  static constexpr int RB = RA >= 4 ? 1 : 4 / RA;           // sub-shifts carried by the B rows
+  static constexpr int TS = RA * RB;                        // taps per tap group (4, 8 or 16)
+  static constexpr int NG = 16 / TS;                        // tap groups = accumulators
+  static constexpr int CO = TS / 4;                         // chunk offset between tap groups
+  static constexpr int NB = C >= 64 ? 128 : (C >= 16 ? C : 16);   // B rows per CTA (= MMA N; C = 8 pads to 16)
   static constexpr int NZ = C == 128 ? 4 : 1;               // CTAs along the sb dimension
-  static constexpr int BCH = 11;                            // B chunks per stage: 8 + 3 (tap groups)
+  static constexpr int BCH = 8 + (NG - 1) * CO;             // B chunks per stage
   static constexpr int A_OP = 8 * 128 * 4, B_OP = BCH * NB * 4;
   static constexpr int STAGE = 2 * A_OP + 2 * B_OP;         // floats
-  static constexpr int NST = C == 32 ? 3 : 2;
+  static constexpr int NST = C >= 64 ? 2 : 3;
+  static constexpr int TM_COLS = NG * NB < 32 ? 32 : NG * NB;
   static constexpr size_t smem = sizeof(float) * ((size_t)STAGE * NST + 3 * 128 + 2 * 128) + 128;
 };
 
 template <int C>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_constant__ WgTcBatch P) {
   using Cfg = CwCfg<C>;
-  constexpr int RA = Cfg::RA, NB = Cfg::NB, BCH = Cfg::BCH, NST = Cfg::NST, A_OP = Cfg::A_OP, B_OP = Cfg::B_OP, STAGE = Cfg::STAGE;
+  constexpr int RA = Cfg::RA, RB = Cfg::RB, TS = Cfg::TS, NG = Cfg::NG, CO = Cfg::CO, NB = Cfg::NB, BCH = Cfg::BCH, NST = Cfg::NST;
+  constexpr int A_OP = Cfg::A_OP, B_OP = Cfg::B_OP, STAGE = Cfg::STAGE;
   const WgJob& J = P.j[blockIdx.y];
   const int L = J.Lo;
-  const int spr = (L + 3 + 31) / 32;                        // stages per batch row (rows shifted by up to 3)
+  const int spr = (L + RA - 1 + 31) / 32;                   // stages per batch row (A rows are shifted by up to RA - 1)
   const int bs = blockIdx.x * P.rows_per_cta, be = min(P.B, bs + P.rows_per_cta);
   if (bs >= be) return;
   const int nstage = (be - bs) * spr;
@@ -257,7 +294,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
   __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_done;
   __shared__ uint32_t tmem_base_s;
   constexpr uint32_t LBO_A = 128 * 16, LBO_B = NB * 16, SBO = 128;
-  constexpr int TM_COLS = 4 * NB;
+  constexpr int TM_COLS = Cfg::TM_COLS;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TM_COLS) : "memory");
@@ -296,8 +333,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t ah = a0 + so + (uint64_t)((ks * 2 * LBO_A) >> 4), al = ah + (uint64_t)((A_OP * 4) >> 4);
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const uint64_t bh = b0 + so + (uint64_t)(((ks * 2 + a) * LBO_B) >> 4), bl = bh + (uint64_t)((B_OP * 4) >> 4);
+          for (int a = 0; a < NG; ++a) {
+            const uint64_t bh = b0 + so + (uint64_t)(((ks * 2 + a * CO) * LBO_B) >> 4), bl = bh + (uint64_t)((B_OP * 4) >> 4);
             const uint32_t acc = tmem_d + a * NB;
             mma_tf32(acc, ah, bh, idesc, (uint32_t)(st | ks));     // first touch overwrites
             mma_tf32(acc, ah, bl, idesc, 1);
@@ -346,9 +383,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
           const int sbl = r / C, ch = r - sbl * C;
           const int pos = p0 + 4 * jc + RA * (sb0 + sbl) - 7;
           const float* rp = rb_ + (long long)ch * L + pos;
+          if (sbl < RB || C == 128) {             // C = 8: rows 8..15 are padding
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (pos + e >= 0 && pos + e < L) xv[i][e] = rp[e];
+            for (int e = 0; e < 4; ++e)
+              if (pos + e >= 0 && pos + e < L) xv[i][e] = rp[e];
+          }
         }
       }
 #pragma unroll
@@ -374,7 +413,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
             float v = xv[i][e];
             if (tin == T_BN_RELU) v = (v - bpar[r]) * bpar[128 + r];
             if (tin == T_RELU || tin == T_BN_RELU) v = v > 0.f ? v : 0.f;
-            a[e] = (pos + e >= 0 && pos + e < L) ? v : 0.f;
+            a[e] = (pos + e >= 0 && pos + e < L && (r / C < RB || C == 128)) ? v : 0.f;
           }
           dst = stage + 2 * A_OP + ((size_t)jc * NB + r) * 4;
         }
@@ -389,25 +428,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
   }
   __syncwarp();
 
-  // ---- epilogue: D_a[(sa, co)][(sb, ci)] -> dW[co][ci][sa + RA sb + 4 a]
+  // ---- epilogue: D_a[(sa, co)][(sb, ci)] -> dW[co][ci][sa + RA sb + TS a]
   mbar_wait(&bar_done, 0);
   tc_fence_after();
   {
     const int q4 = warp & 3;
     const int row = 32 * q4 + lane;
     const int sa = row / C, co = row - sa * C;
-    constexpr int NBLK = NB / 32;
     float* wrow = J.dw + (size_t)co * C * 15;
-    for (int u = (warp >> 2); u < 4 * NBLK; u += 2) {
-      const int a = u / NBLK, blk = u - a * NBLK;
-      float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(a * NB + blk * 32), v);
+    if constexpr (NB >= 32) {
+      constexpr int NBLK = NB / 32;
+      for (int u = (warp >> 2); u < NG * NBLK; u += 2) {
+        const int a = u / NBLK, blk = u - a * NBLK;
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(a * NB + blk * 32), v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = blk * 32 + i;
-        const int sbl = col / C, ci = col - sbl * C;
-        const int t = sa + RA * (sb0 + sbl) + 4 * a;
-        if (t < 15) atomicAdd(wrow + (size_t)ci * 15 + t, v[i]);
+        for (int i = 0; i < 32; ++i) {
+          const int col = blk * 32 + i;
+          const int sbl = col / C, ci = col - sbl * C;
+          const int t = sa + RA * (sb0 + sbl) + TS * a;
+          if (t < 15) atomicAdd(wrow + (size_t)ci * 15 + t, v[i]);
+        }
+      }
+    } else if (warp < 4) {
+      float v[32];                                            // all NG * NB <= 32 accumulator columns at once
+      tmem_ld32(tmem_d + ((uint32_t)(32 * q4) << 16), v);
+#pragma unroll
+      for (int i = 0; i < NG * NB; ++i) {
+        const int a = i / NB, ci = i - a * NB;
+        const int t = sa + TS * a;
+        if (ci < C && t < 15) atomicAdd(wrow + (size_t)ci * 15 + t, v[i]);
       }
     }
   }
@@ -424,7 +474,7 @@ static void launch_conv_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* na
   using Cfg = CwCfg<C>;
   static bool prepared = false;
   if (!prepared) { cudaFuncSetAttribute(k_conv_wgrad_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem); prepared = true; }
-  const int L = b.j[0].Lo, spr = (L + 3 + 31) / 32;
+  const int L = b.j[0].Lo, spr = (L + Cfg::RA - 1 + 31) / 32;
   int rows = 10 / spr;                       // ~10 stages (= 40 k-steps) per accumulation chain
   rows = rows < 1 ? 1 : rows;
   b.rows_per_cta = rows;
@@ -435,7 +485,7 @@ static void launch_conv_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* na
 
 // jobs must share (Cout = Cin = C, stride 1, Lo = Lin)
 static inline bool conv_wgrad_tc_supported(const WgBatch& b) {
-  if (!(b.Cout == 32 || b.Cout == 64 || b.Cout == 128)) return false;
+  if (!wgrad_tc_channels(b.Cout)) return false;
   for (int i = 0; i < b.n; ++i) {
     const WgJob& j = b.j[i];
     if (j.Cin != b.Cout || j.Lo != j.Lin || j.Lo != b.j[0].Lo) return false;
@@ -449,6 +499,8 @@ static int launch_conv_wgrad_tc(WgBatch& b, cudaStream_t st) {
   WgTcBatch t; t.n = b.n; t.B = b.B;
   for (int i = 0; i < b.n; ++i) t.j[i] = b.j[i];
   switch (b.Cout) {
+    case 8: launch_conv_wgrad_tc_t<8>(t, st, "k_conv_wgrad_tc<8>"); break;
+    case 16: launch_conv_wgrad_tc_t<16>(t, st, "k_conv_wgrad_tc<16>"); break;
     case 32: launch_conv_wgrad_tc_t<32>(t, st, "k_conv_wgrad_tc<32>"); break;
     case 64: launch_conv_wgrad_tc_t<64>(t, st, "k_conv_wgrad_tc<64>"); break;
     default: launch_conv_wgrad_tc_t<128>(t, st, "k_conv_wgrad_tc<128>"); break;
