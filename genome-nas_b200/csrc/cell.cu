@@ -607,13 +607,13 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     auto pw_dx = [&](DxBatch& b) { return tc_pw_on(C) ? launch_conv_dx_tc(b, 1, c.st) : launch_dense_dx(1, 1, b, c.st); };
     auto conv_wg = [&](WgBatch& b, int stride) {
 #ifndef GNAS_EMUL
-      if (tc_on(C, stride) && tc_part(5) && tc::conv_wgrad_tc_supported(b)) return tc::launch_conv_wgrad_tc(b, c.st);
+      if (tc_enabled() && stride == 1 && tc_part(5) && tc::conv_wgrad_tc_supported(b)) return tc::launch_conv_wgrad_tc(b, c.st);
 #endif
       return launch_conv_wgrad(15, stride, 7, b, c.st);
     };
     auto pw_wg = [&](WgBatch& b) {
 #ifndef GNAS_EMUL
-      if (tc_on(C, 1) && tc_part(4) && tc::pw_wgrad_tc_supported(b)) return tc::launch_pw_wgrad_tc(b, c.st);
+      if (tc_enabled() && tc_part(4) && tc::pw_wgrad_tc_supported(b)) return tc::launch_pw_wgrad_tc(b, c.st);
 #endif
       return launch_pw_wgrad(1, b, c.st);
     };

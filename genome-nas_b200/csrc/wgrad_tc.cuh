@@ -269,7 +269,8 @@ template <int C> struct CwCfg {
   static constexpr int A_OP = 8 * 128 * 4, B_OP = BCH * NB * 4;
   static constexpr int STAGE = 2 * A_OP + 2 * B_OP;         // floats
   static constexpr int NST = C >= 64 ? 2 : 3;
-  static constexpr int TM_COLS = NG * NB < 32 ? 32 : NG * NB;
+  static constexpr int NV = NG * NB * 4 <= 512 ? 4 : 1;     // accumulator variants: hi*hi rotates over 3, cross terms get 1
+  static constexpr int TM_COLS = NV * NG * NB < 32 ? 32 : NV * NG * NB;
   static constexpr size_t smem = sizeof(float) * ((size_t)STAGE * NST + 3 * 128 + 2 * 128) + 128;
 };
 
@@ -277,7 +278,7 @@ template <int C>
 __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_constant__ WgTcBatch P) {
   using Cfg = CwCfg<C>;
   constexpr int RA = Cfg::RA, RB = Cfg::RB, TS = Cfg::TS, NG = Cfg::NG, CO = Cfg::CO, NB = Cfg::NB, BCH = Cfg::BCH, NST = Cfg::NST;
-  constexpr int A_OP = Cfg::A_OP, B_OP = Cfg::B_OP, STAGE = Cfg::STAGE;
+  constexpr int A_OP = Cfg::A_OP, B_OP = Cfg::B_OP, STAGE = Cfg::STAGE, NV = Cfg::NV;
   const WgJob& J = P.j[blockIdx.y];
   const int L = J.Lo;
   const int spr = (L + RA - 1 + 31) / 32;                   // stages per batch row (A rows are shifted by up to RA - 1)
@@ -335,10 +336,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
 #pragma unroll
           for (int a = 0; a < NG; ++a) {
             const uint64_t bh = b0 + so + (uint64_t)(((ks * 2 + a * CO) * LBO_B) >> 4), bl = bh + (uint64_t)((B_OP * 4) >> 4);
-            const uint32_t acc = tmem_d + a * NB;
-            mma_tf32(acc, ah, bh, idesc, (uint32_t)(st | ks));     // first touch overwrites
-            mma_tf32(acc, ah, bl, idesc, 1);
-            mma_tf32(acc, al, bh, idesc, 1);
+            if constexpr (NV == 1) {
+              const uint32_t acc = tmem_d + a * NB;
+              mma_tf32(acc, ah, bh, idesc, (uint32_t)(st | ks));     // first touch overwrites
+              mma_tf32(acc, ah, bl, idesc, 1);
+              mma_tf32(acc, al, bh, idesc, 1);
+            } else {
+              // room in TMEM: hi*hi rotates over three accumulators, the cross terms share a fourth (shorter
+              // truncating accumulation chains, as in the forward kernels)
+              const int unit = st * 4 + ks;
+              mma_tf32(tmem_d + ((unit % 3) * NG + a) * NB, ah, bh, idesc, (uint32_t)(unit >= 3));
+              mma_tf32(tmem_d + (3 * NG + a) * NB, ah, bl, idesc, (uint32_t)(unit > 0));
+              mma_tf32(tmem_d + (3 * NG + a) * NB, al, bh, idesc, 1);
+            }
           }
         }
         mma_commit(&bar_empty[s]);
@@ -441,7 +451,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
       for (int u = (warp >> 2); u < NG * NBLK; u += 2) {
         const int a = u / NBLK, blk = u - a * NBLK;
         float v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(a * NB + blk * 32), v);
+        const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(a * NB + blk * 32);
+        tmem_ld32(taddr, v);
+#pragma unroll
+        for (int vv = 1; vv < NV; ++vv) {
+          float t[32];
+          tmem_ld32(taddr + vv * NG * NB, t);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += t[i];
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int col = blk * 32 + i;
@@ -451,13 +469,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
         }
       }
     } else if (warp < 4) {
-      float v[32];                                            // all NG * NB <= 32 accumulator columns at once
-      tmem_ld32(tmem_d + ((uint32_t)(32 * q4) << 16), v);
+      constexpr int NC = NG * NB;                             // accumulator columns per variant (16 or 32)
+      constexpr int NLD = (NV * NC + 31) / 32;
+      float v[NLD][32];
 #pragma unroll
-      for (int i = 0; i < NG * NB; ++i) {
+      for (int k = 0; k < NLD; ++k) tmem_ld32(tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(32 * k), v[k]);
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        float sum = 0.f;
+#pragma unroll
+        for (int vv = 0; vv < NV; ++vv) sum += v[(vv * NC + i) / 32][(vv * NC + i) % 32];
         const int a = i / NB, ci = i - a * NB;
         const int t = sa + TS * a;
-        if (ci < C && t < 15) atomicAdd(wrow + (size_t)ci * 15 + t, v[i]);
+        if (ci < C && t < 15) atomicAdd(wrow + (size_t)ci * 15 + t, sum);
       }
     }
   }
