@@ -98,6 +98,7 @@ template <int C, int KW> struct TcCfg {
   static constexpr int TT = KW == 1 ? (C == 128 ? 4 : C / 8) : (C == 32 ? 5 : 3);   // units per weight chunk
   static constexpr int NST = KW == 1 ? (C == 128 ? 2 : 1) : (C == 32 ? 4 : 3);      // weight stages in shared memory
   static constexpr int NCH = NU / TT;
+  static constexpr int NH = NU < 3 ? NU : 3;               // accumulators the hi*hi products rotate over
   static constexpr int W_UNIT = 2 * C * 4;                 // floats of one unit (2 core-matrix columns x C rows), hi or lo
   static constexpr int W_CHUNK = TT * W_UNIT;
   static constexpr int A_HALF = (C / 4) * ROWS * 4;        // floats of A_hi (= A_lo)
@@ -200,8 +201,8 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
           const uint64_t bh = bhc + (uint64_t)((t * W_UNIT * 4) >> 4), bl = blc + (uint64_t)((t * W_UNIT * 4) >> 4);
           // hi*hi products rotate over accumulators 0..2 (fewer sequential fp32 accumulations per accumulator:
           // the tensor core truncates when it adds), the small cross terms share accumulator 3
-          const int am = unit % 3;
-          mma_tf32(tmem_d + am * C, ah, bh, idesc, (uint32_t)(unit >= 3));   // first touch overwrites
+          const int am = unit % Cfg::NH;
+          mma_tf32(tmem_d + am * C, ah, bh, idesc, (uint32_t)(unit >= Cfg::NH));   // first touch overwrites
           mma_tf32(tmem_d + 3 * C, ah, bl, idesc, (uint32_t)(unit > 0));
           mma_tf32(tmem_d + 3 * C, al, bh, idesc, 1);
         }
@@ -296,47 +297,60 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
       for (int c0 = col_base; c0 < col_base + CPW; c0 += 32) {
         float v[32];
         const uint32_t taddr = tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0;
-        tmem_ld32(taddr, v);
+        constexpr int NV = C < 32 ? C : 32;                 // valid channels of this 32-column block
+        if constexpr (C >= 32) {
+          tmem_ld32(taddr, v);
 #pragma unroll
-        for (int a = 1; a < kNAcc; ++a) {
-          float t[32];
-          tmem_ld32(taddr + a * C, t);
+          for (int a = 1; a < kNAcc; ++a) {
+            if (a >= Cfg::NH && a != kNAcc - 1) continue;       // accumulator never written (fewer than 3 units)
+            float t[32];
+            tmem_ld32(taddr + a * C, t);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += t[i];
+            for (int i = 0; i < 32; ++i) v[i] += t[i];
+          }
+        } else {
+          // C = 16: the four accumulators are the 16-column quarters of 64 allocated columns
+          float t0[32], t1[32];
+          tmem_ld32(taddr, t0);
+          tmem_ld32(taddr + 32, t1);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = i < C ? (t0[i] + t0[C + i]) + ((Cfg::NH > 2 ? t1[i] : 0.f) + t1[C + i]) : 0.f;
         }
         float q[32];
         if (omode == O_STORE) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             v[i] = valid ? v[i] : 0.f;
-            if (valid) zrow[(long long)(c0 + i) * L] = v[i];
+            if (valid && i < NV) zrow[(long long)(c0 + i) * L] = v[i];
             q[i] = v[i] * v[i];
           }
         } else if (omode == O_RELU_ACC) {
           float xr[32], old[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            xr[i] = valid ? mrow[(long long)(c0 + i) * L] : 0.f;
-            old[i] = valid ? zrow[(long long)(c0 + i) * L] : 0.f;
+            xr[i] = (valid && i < NV) ? mrow[(long long)(c0 + i) * L] : 0.f;
+            old[i] = (valid && i < NV) ? zrow[(long long)(c0 + i) * L] : 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (valid && xr[i] > 0.f) zrow[(long long)(c0 + i) * L] = old[i] + v[i];
+            if (valid && i < NV && xr[i] > 0.f) zrow[(long long)(c0 + i) * L] = old[i] + v[i];
         } else {   // O_BNRELU_STORE
           float zi[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) zi[i] = valid ? mrow[(long long)(c0 + i) * L] : 0.f;
+          for (int i = 0; i < 32; ++i) zi[i] = (valid && i < NV) ? mrow[(long long)(c0 + i) * L] : 0.f;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            v[i] = (valid && zi[i] > smean[c0 + i]) ? v[i] : 0.f;
-            if (valid) zrow[(long long)(c0 + i) * L] = v[i];
+            v[i] = (valid && i < NV && zi[i] > smean[i < NV ? c0 + i : 0]) ? v[i] : 0.f;
+            if (valid && i < NV) zrow[(long long)(c0 + i) * L] = v[i];
             q[i] = v[i] * zi[i];
           }
         }
         if (stats && omode != O_RELU_ACC) {
           const float s = warp_transpose_sum(v, lane), qq = warp_transpose_sum(q, lane);
-          atomicAdd(&ssum[c0 + lane], s);
-          atomicAdd(&ssum[C + c0 + lane], qq);
+          if (lane < NV) {
+            atomicAdd(&ssum[c0 + lane], s);
+            atomicAdd(&ssum[C + c0 + lane], qq);
+          }
         }
       }
     }
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
   TC_MARK(6);
 }
 
-static inline bool tc_supported(int C) { return C == 32 || C == 64 || C == 128; }
+static inline bool tc_supported(int C) { return C == 16 || C == 32 || C == 64 || C == 128; }
 
 template <int C, int KW>
 static void launch_conv_tc_t(const TcBatch& b, dim3 grid, cudaStream_t st, const char* name) {
@@ -372,6 +386,8 @@ static int launch_conv_tc(TcBatch& b, cudaStream_t st) {
   dim3 grid(tiles, 1, b.n);
   const int key = b.C * 100 + b.KW;
   switch (key) {
+    case 1615: launch_conv_tc_t<16, 15>(b, grid, st, "k_conv_tc<16,15>"); break;
+    case 1601: launch_conv_tc_t<16, 1>(b, grid, st, "k_conv_tc<16,1>"); break;
     case 3215: launch_conv_tc_t<32, 15>(b, grid, st, "k_conv_tc<32,15>"); break;
     case 6415: launch_conv_tc_t<64, 15>(b, grid, st, "k_conv_tc<64,15>"); break;
     case 12815: launch_conv_tc_t<128, 15>(b, grid, st, "k_conv_tc<128,15>"); break;
