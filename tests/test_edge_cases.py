@@ -133,3 +133,84 @@ def test_stem_full_width_alignment(backend):
     assert relerr(y, yr) < 1e-5
     for (n, p), (_, q) in zip(stem.named_parameters(), ref.named_parameters()):
         assert relerr(p.grad, q.grad) < 5e-5, n
+
+
+# ---------------------------------------------------------------- shapes that take the tcgen05 kernels on the GPU
+def _shapes_cell(module, prefix):
+    return _shapes(module, prefix)
+
+
+@pytest.mark.parametrize("C,L,stride", [(32, 60, 1), (64, 45, 2)])
+def test_wide_mixedop_eval_mode(backend, C, L, stride):
+    """eval(): running statistics, no batch statistics accumulated (acc = null in the conv epilogues)."""
+    switch = [True] * 9
+    m = G.MixedOp(C, stride, switch, 0.0)
+    P = O.synthetic_params(_shapes(m, "cell_ops.0."), 8)
+    for k in list(P):
+        if k.endswith("running_var"):
+            P[k] = P[k] * 1.3
+        if k.endswith("running_mean"):
+            P[k] = P[k] + 0.02
+    m.load_state_dict({k[len("cell_ops.0."):]: v for k, v in P.items()})
+    m.to(backend).eval()
+    torch.manual_seed(C + L)
+    x0, w0 = torch.randn(3, C, L), torch.softmax(torch.randn(9), 0)
+    with torch.no_grad():
+        y = m(x0.to(backend), w0.to(backend))
+        Q = {k: v.double() if v.is_floating_point() else v for k, v in P.items()}
+        yo = O.mixed_op(x0.double(), w0.double(), switch, stride, Q, "cell_ops.0", training=False)
+    assert relerr(y, yo) < 1e-5
+    assert all(int(v) == 0 for k, v in m.state_dict().items() if k.endswith("num_batches_tracked"))
+
+
+def test_wide_mixedop_alpha_only_pass(backend):
+    """need_wgrad = 0 (Architect step): dX and d(mix weights) only, no weight-gradient kernel runs."""
+    switch = [True] * 9
+    m = G.MixedOp(32, 1, switch, 0.0)
+    P = O.synthetic_params(_shapes(m, "cell_ops.0."), 9)
+    m.load_state_dict({k[len("cell_ops.0."):]: v for k, v in P.items()})
+    m.to(backend).train()
+    m._wgrad_enabled = False
+    torch.manual_seed(77)
+    x0, w0 = torch.randn(5, 32, 42), torch.softmax(torch.randn(9), 0)      # 42 positions: batch rows packed per tile
+    x, w = leaf(x0, backend), leaf(w0, backend)
+    y = m(x, w)
+    gy = torch.randn(y.shape)
+    (y * gy.to(backend)).sum().backward()
+    yo, xo, wo, Q = _oracle_mixed(m, x0, w0, switch, 1, P)
+    (yo * gy.double()).sum().backward()
+    assert relerr(y, yo) < 1e-5
+    assert relerr(x.grad, xo.grad) < 5e-5
+    assert relerr(w.grad, wo.grad) < 5e-5
+    assert all(p.grad is None for p in m.parameters())
+
+
+def test_wide_search_cell_matches_oracle(backend):
+    """A reduction cell at C = 32 (strided SIMT first convs + tcgen05 second convs / pointwise / weight gradients)."""
+    if backend != "cuda":
+        pytest.skip("emulator: covered by the small golden cells")
+    torch.manual_seed(11)
+    sw = [[True] * 9 for _ in range(14)]
+    m = G.CNN_Cell_search(4, 4, 48, 64, 32, True, False, sw, 0.0, False)
+    shapes = _shapes(m, "cells.0.")
+    P = O.synthetic_params(shapes, 12)
+    m.load_state_dict({k[len("cells.0."):]: v for k, v in P.items()})
+    m.to(backend).train()
+    B, L = 3, 90
+    s00, s10 = torch.randn(B, 48, L), torch.randn(B, 64, L)
+    al0 = 0.5 * torch.randn(14, 9)
+    s0, s1, al = leaf(s00, backend), leaf(s10, backend), leaf(al0, backend)
+    y = m(s0, s1, torch.softmax(al, -1))
+    gy = torch.randn(y.shape)
+    (y * gy.to(backend)).sum().backward()
+    Q = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in P.items()}
+    s0o, s1o, alo = s00.double().requires_grad_(True), s10.double().requires_grad_(True), al0.double().requires_grad_(True)
+    geom = O.CellGeom(index=0, C_pp=48, C_p=64, C=32, reduction=True, reduction_prev=False, stride=2)
+    yo = O.cell_forward(s0o, s1o, torch.softmax(alo, -1), geom, sw, Q, "cells.0", training=True, rec=O.Recorder())
+    (yo * gy.double()).sum().backward()
+    assert relerr(y, yo) < 1e-5
+    assert relerr(s0.grad, s0o.grad) < 5e-5
+    assert relerr(s1.grad, s1o.grad) < 5e-5
+    assert relerr(al.grad, alo.grad) < 5e-5
+    for n, p in m.named_parameters():
+        assert relerr(p.grad, Q["cells.0." + n].grad) < 5e-5, n
