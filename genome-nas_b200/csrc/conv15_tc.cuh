@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
   constexpr int A_HALF = Cfg::A_HALF, W_CHUNK = Cfg::W_CHUNK, W_UNIT = Cfg::W_UNIT;
   constexpr uint32_t LBO_A = ROWS * 16, SBO = 128, LBO_B = C * 16;
   constexpr int TM_COLS = kNAcc * C;
-  constexpr int NLD = kTcThreads - 64;                      // activation-tile threads (warps 2..7)
+  // activation-tile threads: warps 2..7; for the pointwise kernel (one or few weight chunks, nothing to overlap)
+  // the producer and MMA warps help building the tile first
+  constexpr int NLD = KW == 1 ? kTcThreads : kTcThreads - 64, LT0 = kTcThreads - NLD;
   const TcJob& J = P.j[blockIdx.z];
   const int L = J.L;
   const TcTiling tl(L, KW);
@@ -162,11 +164,11 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
   TC_MARK(1);
   const uint32_t tmem_d = tmem_base_s;
 
-  if (warp == 1) {
+  auto produce = [&](int c_begin, int c_end) {
     // ---- weight producer: chunk c = (group g, tap group) is W_CHUNK contiguous floats in each of the hi / lo halves
     const float* whi = J.w;
     const float* wlo = J.w + (long long)C * C * KW;
-    for (int c = 0; c < NCH; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       const int s = c % NST;
       if (c >= NST) mbar_wait(&bar_empty[s], ((c / NST) - 1) & 1);
       if (elect_one()) {
@@ -177,7 +179,8 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
       }
       __syncwarp();
     }
-  } else if (warp == 0) {
+  };
+  auto mma_loop = [&]() {
     // ---- MMA issuer: the whole warp runs the loop (descriptors stay in uniform registers), one elected lane issues
     const uint32_t idesc = make_idesc(C);
     const uint64_t ah0 = make_desc(smem_u32(A_hi), LBO_A, SBO), al0 = make_desc(smem_u32(A_lo), LBO_A, SBO);
@@ -214,7 +217,8 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
     if (elect_one()) mma_commit(&bar_done);
     __syncwarp();
     TC_MARK(3);
-  } else if (warp >= 2) {
+  };
+  auto a_load = [&]() {
     // ---- activation tile: row p <-> (batch row, position - 7), transformed, split into tf32 hi / lo.
     //      One item = 4 channels of one row = one 16-byte core-matrix row: conflict-free vector stores,
     //      global loads coalesced along the row index; 4 items (16-32 loads) in flight per thread.
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
     const int tin = J.tin;
     const bool affine = tin < 0 && J.x2 != nullptr;
     int garr = 0;
-    for (int base = tid - 64; base < NIT; base += UN * NLD) {
+    for (int base = tid - LT0; base < NIT; base += UN * NLD) {
       float xv[UN][4], yv[UN][4];
       int kcs[UN];
 #pragma unroll
@@ -273,7 +277,13 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
       while (garr < G && (garr + 1) * GI <= nxt) { fence_async_smem(); mbar_arrive(&bar_a[garr]); ++garr; }
     }
     while (garr < G) { fence_async_smem(); mbar_arrive(&bar_a[garr]); ++garr; }
-  }
+  };
+  constexpr int NPRE = NCH < NST ? NCH : NST;      // chunks that need no free-stage wait
+  if (warp == 1) produce(0, NPRE);
+  if (KW == 1 || warp >= 2) a_load();
+  __syncwarp();
+  if (warp == 1) produce(NPRE, NCH);
+  else if (warp == 0) mma_loop();
   __syncwarp();
 
   // ---- epilogue: TMEM -> registers -> global (+ per-channel statistics)
