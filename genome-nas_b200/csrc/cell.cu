@@ -63,10 +63,10 @@ inline bool tc_on(int C, int stride) {
 }
 // debugging aid: GNAS_TC_PART bit 0 = conv_15 forward, bit 1 / 2 = data gradient of its second / first conv,
 // bit 3 = pointwise convs (forward and data gradient), bit 4 = pointwise weight gradient,
-// bit 5 = conv_15 weight gradient
+// bit 5 = conv_15 weight gradient, bit 6 = strided conv_15 data gradient
 inline bool tc_part(int bit) {
   static int v = -1;
-  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 63; }
+  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 127; }
   return (v >> bit) & 1;
 }
 #ifndef GNAS_EMUL
@@ -79,6 +79,7 @@ int launch_conv_fwd_tc(DenseBatch& db, int KW, cudaStream_t st) {
     t.x = j.x; t.xbs = j.xbs; t.x2 = nullptr; t.x2bs = 0; t.in_stat = j.in_stat; t.w = j.wp;
     t.z = j.z; t.zbs = j.zbs; t.acc = j.acc; t.mref = nullptr; t.mrbs = 0; t.mstat = nullptr;
     t.L = j.Lout; t.tin = j.tin; t.omode = O_STORE;
+    t.zl = t.L; t.zs = 1; t.zo = 0; t.halo = -1;
   }
   db.n = 0;
   return tc::launch_conv_tc(tb, st);
@@ -92,9 +93,37 @@ int launch_conv_dx_tc(DxBatch& xb, int KW, cudaStream_t st) {
     t.z = j.out; t.zbs = j.obs; t.acc = j.omode == O_BNRELU_STORE ? j.bacc : nullptr;
     t.mref = j.xin; t.mrbs = j.xibs; t.mstat = j.xin_stat;
     t.L = j.Lo; t.tin = -1; t.omode = j.omode;
+    t.zl = t.L; t.zs = 1; t.zo = 0; t.halo = -1;
   }
   xb.n = 0;
   return tc::launch_conv_tc(tb, st);
+}
+// Data gradient of a stride-S conv_15: the outputs m = S q + rho of each residue class rho are a stride-1
+// correlation over dz with the taps t = (rho + 7) mod S + S k (5 per class for S = 3; 7 / 8, padded to 8, for S = 2);
+// one tensor-core job per (conv, class), weights packed per class by k_pack_tc mode 2.
+inline int strided_dx_taps(int S) { return S == 3 ? 5 : 8; }
+inline long long strided_dx_pack_floats(int C, int S) { return 2LL * C * C * strided_dx_taps(S) * S; }
+int launch_conv_dx_strided_tc(DxBatch& xb, int S, cudaStream_t st) {
+  const int NT = strided_dx_taps(S);
+  tc::TcBatch tb; tb.n = 0; tb.B = xb.B; tb.C = xb.Cin; tb.KW = NT;
+  int rc = 0;
+  for (int i = 0; i < xb.n; ++i) {
+    const DxJob& j = xb.j[i];
+    for (int rho = 0; rho < S; ++rho) {
+      const int t0 = (rho + 7) % S, D0 = (rho + 7 - t0) / S;
+      tc::TcJob& t = tb.j[tb.n++];
+      t.x = j.g; t.xbs = j.gbs; t.x2 = j.z; t.x2bs = j.zbs; t.in_stat = j.coef;
+      t.w = j.wt + (long long)rho * 2 * xb.Cin * xb.Cin * NT;
+      t.z = j.out; t.zbs = j.obs; t.acc = nullptr;
+      t.mref = j.xin; t.mrbs = j.xibs; t.mstat = nullptr;
+      t.L = j.Lo; t.tin = -1; t.omode = j.omode;
+      t.zl = j.Lin; t.zs = S; t.zo = rho; t.halo = NT - 1 - D0;
+      if (tb.n == kMaxDense) rc |= tc::launch_conv_tc(tb, st);
+    }
+  }
+  xb.n = 0;
+  rc |= tc::launch_conv_tc(tb, st);
+  return rc;
 }
 void pack_tc(tc::TcPackBatch& pb, cudaStream_t st) {
   if (pb.n == 0) return;
@@ -104,9 +133,18 @@ void pack_tc(tc::TcPackBatch& pb, cudaStream_t st) {
 #else
 int launch_conv_fwd_tc(DenseBatch&, int, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
 int launch_conv_dx_tc(DxBatch&, int, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
+int launch_conv_dx_strided_tc(DxBatch&, int, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
+inline long long strided_dx_pack_floats(int, int) { return 0; }
 #endif
 inline bool tc_fwd_on(int C, int stride) { return tc_on(C, stride) && tc_part(0); }
 inline bool tc_dx_on(int C, int stride, int conv) { return tc_on(C, stride) && tc_part(conv == 1 ? 1 : 2); }
+inline bool tc_sdx_on(int C, int S) {       // strided conv_15 data gradient: instantiated for the supernet's reduction cells
+#ifdef GNAS_EMUL
+  (void)C; (void)S; return false;
+#else
+  return tc_enabled() && tc_part(6) && ((S == 2 && (C == 32 || C == 64)) || (S == 3 && C == 128));
+#endif
+}
 inline bool tc_pw_on(int C) { return tc_on(C, 1) && tc_part(3); }
 inline long long pw_pack_floats(int C) { return (long long)C * C * (tc_pw_on(C) ? 2 : 1); }
 inline long long conv15_pack_floats(int C) { return (long long)C * C * 15 * (tc_on(C, 1) ? 2 : 1); }
@@ -207,7 +245,11 @@ void make_plan(const GnasCellDesc* d, CellPlan& P) {
     for (int i = 0; i < 9; ++i) { P.tmp[s][i] = o; o += al4(P.nCL_out); }
   for (int e = 0; e < d->n_edges; ++e) {
     OpPlan& O = P.e[e].op[GNAS_CONV15];
-    if (O.on) for (int i = 0; i < 2; ++i) { O.pkb[i] = o; o += al4(conv15_pack_floats(C)); }
+    if (O.on) for (int i = 0; i < 2; ++i) {
+      long long n = conv15_pack_floats(C);
+      if (i == 0 && tc_sdx_on(C, P.e[e].stride)) { const long long m = strided_dx_pack_floats(C, P.e[e].stride); n = m > n ? m : n; }
+      O.pkb[i] = o; o += al4(n);
+    }
     if (tc_pw_on(C)) {   // tensor-core data gradient of the pointwise convs: transposed hi | lo packs
       const int ks[4] = {GNAS_SEP15, GNAS_SEP9, GNAS_DIL15, GNAS_DIL9};
       for (int v = 0; v < 4; ++v) {
@@ -766,7 +808,8 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         w.Cin = C; w.Lo = Lo; w.Lin = Lin; w.tin = T_RELU;
       }
     }
-    c.rc |= tc_dx_on(C, S, 0) ? launch_conv_dx_tc(xb, 15, c.st) : launch_dense_dx(15, S, xb, c.st);
+    c.rc |= tc_dx_on(C, S, 0) ? launch_conv_dx_tc(xb, 15, c.st)
+            : (S > 1 && tc_sdx_on(C, S)) ? launch_conv_dx_strided_tc(xb, S, c.st) : launch_dense_dx(15, S, xb, c.st);
     c.rc |= conv_wg(gb, S);
   }
 }
@@ -826,6 +869,18 @@ void pack_backward(Ctx& c) {
     if (!O.on) continue;
     for (int i = 0; i < 2; ++i) {
       const int cs = i == 0 ? c.P.e[e].stride : 1;
+#ifndef GNAS_EMUL
+      if (i == 0 && cs > 1 && tc_sdx_on(C, cs)) {
+        const int NT = strided_dx_taps(cs);
+        for (int rho = 0; rho < cs; ++rho) {
+          tc::TcPackJob& t = tp.j[tp.n++];
+          t.src = c.W(e, GNAS_CONV15, 0); t.dst = c.scratch + O.pkb[0] + (long long)rho * 2 * C * C * NT;
+          t.C = C; t.mode = 2; t.KW = NT; t.S = cs; t.rho = rho;
+          if (tp.n == 64) pack_tc(tp, c.st);
+        }
+        continue;
+      }
+#endif
       if (tc_dx_on(C, cs, i)) {
 #ifndef GNAS_EMUL
         tc::TcPackJob& t = tp.j[tp.n++];

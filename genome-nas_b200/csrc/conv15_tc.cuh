@@ -23,15 +23,27 @@ namespace tc {
 // dst[half][g][tap][kc][n][e]  (g: group of 8 reduction channels, kc: 4-channel core matrix, n: output row, e: 0..3)
 // mode 0 (forward): n = co, reduction channel = ci, tap as is;   mode 1 (data gradient): n = ci, reduction = co,
 // tap flipped (out[m] = sum_t W[.,.,t] dz[m + pad - t]  ==  conv with taps t' = KW - 1 - t).
-struct TcPackJob { const float* src; float* dst; int C, mode, KW; };
+struct TcPackJob { const float* src; float* dst; int C, mode, KW, S, rho; };   // mode 2: residue class rho of a stride-S data gradient
 struct TcPackBatch { int n; TcPackJob j[64]; };
 static __global__ void __launch_bounds__(256) k_pack_tc(const __grid_constant__ TcPackBatch P) {
   const TcPackJob& J = P.j[blockIdx.y];
   const int C = J.C, KW = J.KW, total = C * C * KW;
+  // mode 2: data gradient of a stride-S conv_15 restricted to output positions m = S q + rho.  Only the taps
+  // t = t0 + S k (t0 = (rho + 7) mod S) reach them; written as a stride-1 correlation over dz with KW taps,
+  // tap k' uses t = t0 + S (KW - 1 - k')  (t > 14: zero weight pads the class to KW taps).
+  const int t0 = J.mode == 2 ? (J.rho + 7) % J.S : 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int t = i % KW, ci = (i / KW) % C, co = i / (KW * C);
-    const float w = J.src[i];
-    const int n = J.mode == 0 ? co : ci, r = J.mode == 0 ? ci : co, tap = J.mode == 0 ? t : KW - 1 - t;
+    float w;
+    int n, r, tap;
+    if (J.mode == 2) {
+      const int tt = t0 + J.S * (KW - 1 - t);
+      w = tt <= 14 ? J.src[((long long)co * C + ci) * 15 + tt] : 0.f;
+      n = ci; r = co; tap = t;
+    } else {
+      w = J.src[i];
+      n = J.mode == 0 ? co : ci; r = J.mode == 0 ? ci : co; tap = J.mode == 0 ? t : KW - 1 - t;
+    }
     const int g = r >> 3, kc = (r >> 2) & 1, e = r & 3;
     const long long o = ((((long long)g * KW + tap) * 2 + kc) * C + n) * 4 + e;
     const float hi = __uint_as_float(to_tf32(w));
@@ -58,6 +70,8 @@ struct TcJob {
   const float* mref; long long mrbs;  // epilogue mask reference: x (O_RELU_ACC) or z1 (O_BNRELU_STORE)
   const float* mstat;                 // mean | rstd of the inner BN (O_BNRELU_STORE)
   int L, tin, omode;                  // tin: T_RELU / T_BN_RELU / -1 (affine dz); omode: O_STORE(+stats) / O_RELU_ACC / O_BNRELU_STORE
+  int zl, zs, zo;                     // output (and mref) geometry: row length, position stride and offset (L, 1, 0 unless strided)
+  int halo;                           // input row of output row 0 is position -halo; < 0: (KW - 1) / 2
 };
 struct TcBatch { int n, B, C, KW; TcJob j[kMaxDense]; };
 
@@ -95,8 +109,9 @@ __device__ __forceinline__ float warp_transpose_sum(float (&a)[32], int lane) {
 template <int C, int KW> struct TcCfg {
   static constexpr int ROWS = KW == 1 ? 128 : 144;         // A rows per 4-channel group: 128 outputs + KW-1 halo (+2 pad)
   static constexpr int NU = (C / 8) * KW;                  // MMA units: (group of 8 reduction channels, tap)
-  static constexpr int TT = KW == 1 ? (C == 128 ? 4 : C / 8) : (C == 32 ? 5 : 3);   // units per weight chunk
-  static constexpr int NST = KW == 1 ? (C == 128 ? 2 : 1) : (C == 32 ? 4 : 3);      // weight stages in shared memory
+  // units per weight chunk / weight stages in shared memory (KW = 5, 8: residue classes of the strided data gradient)
+  static constexpr int TT = KW == 1 ? (C == 128 ? 4 : C / 8) : KW == 15 ? (C == 32 ? 5 : 3) : (C == 128 ? 1 : (KW == 5 ? 5 : 4));
+  static constexpr int NST = KW == 1 ? (C == 128 ? 2 : 1) : KW == 15 ? (C == 32 ? 4 : 3) : (C == 128 ? 8 : 3);
   static constexpr int NCH = NU / TT;
   static constexpr int NH = NU < 3 ? NU : 3;               // accumulators the hi*hi products rotate over
   static constexpr int W_UNIT = 2 * C * 4;                 // floats of one unit (2 core-matrix columns x C rows), hi or lo
@@ -113,7 +128,7 @@ template <int C, int KW>
 __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const __grid_constant__ TcBatch P) {
   using Cfg = TcCfg<C, KW>;
   constexpr int G = C / 8;                                  // reduction groups of 8 channels
-  constexpr int TT = Cfg::TT, NCH = Cfg::NCH, NST = Cfg::NST, ROWS = Cfg::ROWS, HALO = (KW - 1) / 2;
+  constexpr int TT = Cfg::TT, NCH = Cfg::NCH, NST = Cfg::NST, ROWS = Cfg::ROWS;
   constexpr int A_HALF = Cfg::A_HALF, W_CHUNK = Cfg::W_CHUNK, W_UNIT = Cfg::W_UNIT;
   constexpr uint32_t LBO_A = ROWS * 16, SBO = 128, LBO_B = C * 16;
   constexpr int TM_COLS = kNAcc * C;
@@ -122,6 +137,7 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
   constexpr int NLD = KW == 1 ? kTcThreads : kTcThreads - 64, LT0 = kTcThreads - NLD;
   const TcJob& J = P.j[blockIdx.z];
   const int L = J.L;
+  const int HALO = J.halo >= 0 ? J.halo : (KW - 1) / 2;
   const TcTiling tl(L, KW);
   const bool packed = tl.nseg > 1;
   if ((int)blockIdx.x >= tl.tiles(P.B)) return;
@@ -298,8 +314,11 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
     constexpr int CPW = C >= 64 ? C / 2 : 32;             // columns per warp (two warps share a TMEM lane quarter)
     const int col_base = C >= 64 ? (warp >> 2) * CPW : 0;
     const bool warp_on = C >= 64 || warp < 4;
-    float* zrow = J.z + (long long)bb * J.zbs + l;
-    const float* mrow = J.mref ? J.mref + (long long)bb * J.mrbs + l : nullptr;
+    const int zpos = J.zs * l + J.zo;
+    const long long ZL = J.zl;                                // channel pitch of z / mref
+    valid = valid && zpos < J.zl;
+    float* zrow = J.z + (long long)bb * J.zbs + zpos;
+    const float* mrow = J.mref ? J.mref + (long long)bb * J.mrbs + zpos : nullptr;
     const int omode = J.omode;
     const bool stats = J.acc != nullptr;
     if (warp_on) {
@@ -331,27 +350,27 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             v[i] = valid ? v[i] : 0.f;
-            if (valid && i < NV) zrow[(long long)(c0 + i) * L] = v[i];
+            if (valid && i < NV) zrow[(long long)(c0 + i) * ZL] = v[i];
             q[i] = v[i] * v[i];
           }
         } else if (omode == O_RELU_ACC) {
           float xr[32], old[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            xr[i] = (valid && i < NV) ? mrow[(long long)(c0 + i) * L] : 0.f;
-            old[i] = (valid && i < NV) ? zrow[(long long)(c0 + i) * L] : 0.f;
+            xr[i] = (valid && i < NV) ? mrow[(long long)(c0 + i) * ZL] : 0.f;
+            old[i] = (valid && i < NV) ? zrow[(long long)(c0 + i) * ZL] : 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (valid && i < NV && xr[i] > 0.f) zrow[(long long)(c0 + i) * L] = old[i] + v[i];
+            if (valid && i < NV && xr[i] > 0.f) zrow[(long long)(c0 + i) * ZL] = old[i] + v[i];
         } else {   // O_BNRELU_STORE
           float zi[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) zi[i] = (valid && i < NV) ? mrow[(long long)(c0 + i) * L] : 0.f;
+          for (int i = 0; i < 32; ++i) zi[i] = (valid && i < NV) ? mrow[(long long)(c0 + i) * ZL] : 0.f;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             v[i] = (valid && i < NV && zi[i] > smean[i < NV ? c0 + i : 0]) ? v[i] : 0.f;
-            if (valid && i < NV) zrow[(long long)(c0 + i) * L] = v[i];
+            if (valid && i < NV) zrow[(long long)(c0 + i) * ZL] = v[i];
             q[i] = v[i] * zi[i];
           }
         }
@@ -401,6 +420,9 @@ static int launch_conv_tc(TcBatch& b, cudaStream_t st) {
     case 3215: launch_conv_tc_t<32, 15>(b, grid, st, "k_conv_tc<32,15>"); break;
     case 6415: launch_conv_tc_t<64, 15>(b, grid, st, "k_conv_tc<64,15>"); break;
     case 12815: launch_conv_tc_t<128, 15>(b, grid, st, "k_conv_tc<128,15>"); break;
+    case 3208: launch_conv_tc_t<32, 8>(b, grid, st, "k_conv_tc<32,8>"); break;
+    case 6408: launch_conv_tc_t<64, 8>(b, grid, st, "k_conv_tc<64,8>"); break;
+    case 12805: launch_conv_tc_t<128, 5>(b, grid, st, "k_conv_tc<128,5>"); break;
     case 3201: launch_conv_tc_t<32, 1>(b, grid, st, "k_conv_tc<32,1>"); break;
     case 6401: launch_conv_tc_t<64, 1>(b, grid, st, "k_conv_tc<64,1>"); break;
     case 12801: launch_conv_tc_t<128, 1>(b, grid, st, "k_conv_tc<128,1>"); break;
