@@ -63,10 +63,10 @@ inline bool tc_on(int C, int stride) {
 }
 // debugging aid: GNAS_TC_PART bit 0 = conv_15 forward, bit 1 / 2 = data gradient of its second / first conv,
 // bit 3 = pointwise convs (forward and data gradient), bit 4 = pointwise weight gradient,
-// bit 5 = conv_15 weight gradient, bit 6 = strided conv_15 data gradient
+// bit 5 = conv_15 weight gradient, bit 6 = strided conv_15 data gradient, bit 7 = strided conv_15 forward
 inline bool tc_part(int bit) {
   static int v = -1;
-  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 127; }
+  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 255; }
   return (v >> bit) & 1;
 }
 #ifndef GNAS_EMUL
@@ -79,7 +79,7 @@ int launch_conv_fwd_tc(DenseBatch& db, int KW, cudaStream_t st) {
     t.x = j.x; t.xbs = j.xbs; t.x2 = nullptr; t.x2bs = 0; t.in_stat = j.in_stat; t.w = j.wp;
     t.z = j.z; t.zbs = j.zbs; t.acc = j.acc; t.mref = nullptr; t.mrbs = 0; t.mstat = nullptr;
     t.L = j.Lout; t.tin = j.tin; t.omode = O_STORE;
-    t.zl = t.L; t.zs = 1; t.zo = 0; t.halo = -1;
+    t.zl = t.L; t.zs = 1; t.zo = 0; t.halo = -1; t.xl = t.L; t.xs = 1; t.xo = 0;
   }
   db.n = 0;
   return tc::launch_conv_tc(tb, st);
@@ -93,7 +93,7 @@ int launch_conv_dx_tc(DxBatch& xb, int KW, cudaStream_t st) {
     t.z = j.out; t.zbs = j.obs; t.acc = j.omode == O_BNRELU_STORE ? j.bacc : nullptr;
     t.mref = j.xin; t.mrbs = j.xibs; t.mstat = j.xin_stat;
     t.L = j.Lo; t.tin = -1; t.omode = j.omode;
-    t.zl = t.L; t.zs = 1; t.zo = 0; t.halo = -1;
+    t.zl = t.L; t.zs = 1; t.zo = 0; t.halo = -1; t.xl = t.L; t.xs = 1; t.xo = 0;
   }
   xb.n = 0;
   return tc::launch_conv_tc(tb, st);
@@ -101,8 +101,32 @@ int launch_conv_dx_tc(DxBatch& xb, int KW, cudaStream_t st) {
 // Data gradient of a stride-S conv_15: the outputs m = S q + rho of each residue class rho are a stride-1
 // correlation over dz with the taps t = (rho + 7) mod S + S k (5 per class for S = 3; 7 / 8, padded to 8, for S = 2);
 // one tensor-core job per (conv, class), weights packed per class by k_pack_tc mode 2.
+// Forward of a stride-S conv_15: the input is split into its S phases x[S q + phi]; each phase is a stride-1
+// correlation with the taps t = (phi + 7) mod S + S k, and the phases are accumulated by S consecutive launches
+// (store, then add; the last one also takes the BN statistics of the finished sum).
+int launch_conv_fwd_strided_tc(DenseBatch& db, int S, cudaStream_t st);
 inline int strided_dx_taps(int S) { return S == 3 ? 5 : 8; }
 inline long long strided_dx_pack_floats(int C, int S) { return 2LL * C * C * strided_dx_taps(S) * S; }
+int launch_conv_fwd_strided_tc(DenseBatch& db, int S, cudaStream_t st) {
+  const int NT = strided_dx_taps(S);
+  int rc = 0;
+  for (int phi = 0; phi < S; ++phi) {
+    tc::TcBatch tb; tb.n = 0; tb.B = db.B; tb.C = db.Cout; tb.KW = NT;
+    const int t0 = (phi + 7) % S;
+    for (int i = 0; i < db.n; ++i) {
+      const DenseJob& j = db.j[i];
+      tc::TcJob& t = tb.j[tb.n++];
+      t.x = j.x; t.xbs = j.xbs; t.x2 = nullptr; t.x2bs = 0; t.in_stat = j.in_stat;
+      t.w = j.wp + (long long)phi * 2 * db.Cout * db.Cout * NT;
+      t.z = j.z; t.zbs = j.zbs; t.acc = phi == S - 1 ? j.acc : nullptr; t.mref = nullptr; t.mrbs = 0; t.mstat = nullptr;
+      t.L = j.Lout; t.tin = j.tin; t.omode = phi == 0 ? O_STORE : O_ACC;
+      t.zl = t.L; t.zs = 1; t.zo = 0; t.halo = (7 + phi - t0) / S; t.xl = j.Lin; t.xs = S; t.xo = phi;
+    }
+    rc |= tc::launch_conv_tc(tb, st);
+  }
+  db.n = 0;
+  return rc;
+}
 int launch_conv_dx_strided_tc(DxBatch& xb, int S, cudaStream_t st) {
   const int NT = strided_dx_taps(S);
   tc::TcBatch tb; tb.n = 0; tb.B = xb.B; tb.C = xb.Cin; tb.KW = NT;
@@ -117,7 +141,7 @@ int launch_conv_dx_strided_tc(DxBatch& xb, int S, cudaStream_t st) {
       t.z = j.out; t.zbs = j.obs; t.acc = nullptr;
       t.mref = j.xin; t.mrbs = j.xibs; t.mstat = nullptr;
       t.L = j.Lo; t.tin = -1; t.omode = j.omode;
-      t.zl = j.Lin; t.zs = S; t.zo = rho; t.halo = NT - 1 - D0;
+      t.zl = j.Lin; t.zs = S; t.zo = rho; t.halo = NT - 1 - D0; t.xl = t.L; t.xs = 1; t.xo = 0;
       if (tb.n == kMaxDense) rc |= tc::launch_conv_tc(tb, st);
     }
   }
@@ -134,6 +158,7 @@ void pack_tc(tc::TcPackBatch& pb, cudaStream_t st) {
 int launch_conv_fwd_tc(DenseBatch&, int, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
 int launch_conv_dx_tc(DxBatch&, int, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
 int launch_conv_dx_strided_tc(DxBatch&, int, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
+int launch_conv_fwd_strided_tc(DenseBatch&, int, cudaStream_t) { return GNAS_ERR_UNSUPPORTED; }
 inline long long strided_dx_pack_floats(int, int) { return 0; }
 #endif
 inline bool tc_fwd_on(int C, int stride) { return tc_on(C, stride) && tc_part(0); }
@@ -145,6 +170,7 @@ inline bool tc_sdx_on(int C, int S) {       // strided conv_15 data gradient: in
   return tc_enabled() && tc_part(6) && ((S == 2 && (C == 32 || C == 64)) || (S == 3 && C == 128));
 #endif
 }
+inline bool tc_sfw_on(int C, int S) { return tc_sdx_on(C, S) && tc_part(7); }
 inline bool tc_pw_on(int C) { return tc_on(C, 1) && tc_part(3); }
 inline long long pw_pack_floats(int C) { return (long long)C * C * (tc_pw_on(C) ? 2 : 1); }
 inline long long conv15_pack_floats(int C) { return (long long)C * C * 15 * (tc_on(C, 1) ? 2 : 1); }
@@ -223,7 +249,10 @@ void make_plan(const GnasCellDesc* d, CellPlan& P) {
         case GNAS_SKIP: if (E.stride > 1) { nt = 1; npk[0] = C * C; } break;
         case GNAS_SEP15: case GNAS_SEP9: nt = 4; npk[0] = npk[1] = (int)pw_pack_floats(C); break;
         case GNAS_DIL15: case GNAS_DIL9: nt = 2; npk[0] = (int)pw_pack_floats(C); break;
-        case GNAS_CONV15: nt = 2; npk[0] = npk[1] = (int)conv15_pack_floats(C); break;
+        case GNAS_CONV15:
+          nt = 2; npk[0] = npk[1] = (int)conv15_pack_floats(C);
+          if (tc_sfw_on(C, E.stride) && strided_dx_pack_floats(C, E.stride) > npk[0]) npk[0] = (int)strided_dx_pack_floats(C, E.stride);
+          break;
         default: break;
       }
       for (int i = 0; i < nt; ++i) { O.t[i] = o; o += al4(P.nCL_out); }
@@ -396,7 +425,8 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     j.Cin = C; j.Lin = Lin; j.Lout = Lo; j.tin = T_RELU;
     fin_add(e, GNAS_CONV15, 0);
   }
-  c.rc |= tc_fwd_on(C, S) ? launch_conv_fwd_tc(db, 15, c.st) : launch_dense_fwd(15, S, db, c.st);
+  c.rc |= tc_fwd_on(C, S) ? launch_conv_fwd_tc(db, 15, c.st)
+          : (S > 1 && tc_sfw_on(C, S)) ? launch_conv_fwd_strided_tc(db, S, c.st) : launch_dense_fwd(15, S, db, c.st);
   finalize(c, fs, fc, fr, nf);
   nf = 0;
   // ---- stage 2 (sep_conv second half, conv_15 second conv) reads BN+ReLU of stage 1 on the fly
@@ -512,6 +542,18 @@ void pack_forward(Ctx& c) {
       if (k == GNAS_CONV15) {
         for (int i = 0; i < 2; ++i) {
           const int cs = i == 0 ? E.stride : 1;
+#ifndef GNAS_EMUL
+          if (i == 0 && cs > 1 && tc_sfw_on(C, cs)) {
+            const int NT = strided_dx_taps(cs);
+            for (int phi = 0; phi < cs; ++phi) {
+              tc::TcPackJob& t = tp.j[tp.n++];
+              t.src = c.W(e, k, 0); t.dst = c.ws + O.pk[0] + (long long)phi * 2 * C * C * NT;
+              t.C = C; t.mode = 3; t.KW = NT; t.S = cs; t.rho = phi;
+              if (tp.n == 64) pack_tc(tp, c.st);
+            }
+            continue;
+          }
+#endif
           if (!tc_fwd_on(C, cs)) { add(c.W(e, k, i), c.ws + O.pk[i], C, C, 15, 0); continue; }
 #ifndef GNAS_EMUL
           tc::TcPackJob& t = tp.j[tp.n++];

@@ -31,7 +31,8 @@ static __global__ void __launch_bounds__(256) k_pack_tc(const __grid_constant__ 
   // mode 2: data gradient of a stride-S conv_15 restricted to output positions m = S q + rho.  Only the taps
   // t = t0 + S k (t0 = (rho + 7) mod S) reach them; written as a stride-1 correlation over dz with KW taps,
   // tap k' uses t = t0 + S (KW - 1 - k')  (t > 14: zero weight pads the class to KW taps).
-  const int t0 = J.mode == 2 ? (J.rho + 7) % J.S : 0;
+  // mode 3: forward of a stride-S conv_15 restricted to the input phase rho (x[S q + rho]): taps t = t0 + S k.
+  const int t0 = J.mode >= 2 ? (J.rho + 7) % J.S : 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int t = i % KW, ci = (i / KW) % C, co = i / (KW * C);
     float w;
@@ -40,6 +41,10 @@ static __global__ void __launch_bounds__(256) k_pack_tc(const __grid_constant__ 
       const int tt = t0 + J.S * (KW - 1 - t);
       w = tt <= 14 ? J.src[((long long)co * C + ci) * 15 + tt] : 0.f;
       n = ci; r = co; tap = t;
+    } else if (J.mode == 3) {
+      const int tt = t0 + J.S * t;
+      w = tt <= 14 ? J.src[((long long)co * C + ci) * 15 + tt] : 0.f;
+      n = co; r = ci; tap = t;
     } else {
       w = J.src[i];
       n = J.mode == 0 ? co : ci; r = J.mode == 0 ? ci : co; tap = J.mode == 0 ? t : KW - 1 - t;
@@ -72,6 +77,7 @@ struct TcJob {
   int L, tin, omode;                  // tin: T_RELU / T_BN_RELU / -1 (affine dz); omode: O_STORE(+stats) / O_RELU_ACC / O_BNRELU_STORE
   int zl, zs, zo;                     // output (and mref) geometry: row length, position stride and offset (L, 1, 0 unless strided)
   int halo;                           // input row of output row 0 is position -halo; < 0: (KW - 1) / 2
+  int xl, xs, xo;                     // input geometry: channel pitch, position stride and offset (L, 1, 0 unless decimated)
 };
 struct TcBatch { int n, B, C, KW; TcJob j[kMaxDense]; };
 
@@ -254,14 +260,16 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
         int bb, pos; bool ok;
         if (packed) { const int sgi = p / tl.seg; bb = b0 + sgi; pos = p - sgi * tl.seg - HALO; ok = sgi < tl.nseg && bb < P.B; }
         else { bb = b0; pos = l0 - HALO + p; ok = p < 128 + KW - 1; }
-        ok = ok && idx < NIT && pos >= 0 && pos < L;
-        const long long off = (long long)(4 * kc) * L + pos;
+        const int xpos = J.xs * pos + J.xo;
+        ok = ok && idx < NIT && pos >= 0 && xpos < J.xl;
+        const long long XL = J.xl;
+        const long long off = (long long)(4 * kc) * XL + xpos;
         const float* xr = J.x + (long long)bb * J.xbs + off;
         const float* yr = affine ? J.x2 + (long long)bb * J.x2bs + off : nullptr;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          xv[u][e] = ok ? xr[(long long)e * L] : 0.f;
-          yv[u][e] = (ok && affine) ? yr[(long long)e * L] : 0.f;
+          xv[u][e] = ok ? xr[(long long)e * XL] : 0.f;
+          yv[u][e] = (ok && affine) ? yr[(long long)e * XL] : 0.f;
         }
         if (!ok) kcs[u] = -1 - kc;
       }
@@ -350,6 +358,16 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             v[i] = valid ? v[i] : 0.f;
+            if (valid && i < NV) zrow[(long long)(c0 + i) * ZL] = v[i];
+            q[i] = v[i] * v[i];
+          }
+        } else if (omode == O_ACC) {          // later phases of a strided forward conv: add to the partial sum
+          float old[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) old[i] = (valid && i < NV) ? zrow[(long long)(c0 + i) * ZL] : 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = valid ? old[i] + v[i] : 0.f;
             if (valid && i < NV) zrow[(long long)(c0 + i) * ZL] = v[i];
             q[i] = v[i] * v[i];
           }
