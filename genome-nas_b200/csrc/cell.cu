@@ -63,10 +63,11 @@ inline bool tc_on(int C, int stride) {
 }
 // debugging aid: GNAS_TC_PART bit 0 = conv_15 forward, bit 1 / 2 = data gradient of its second / first conv,
 // bit 3 = pointwise convs (forward and data gradient), bit 4 = pointwise weight gradient,
-// bit 5 = conv_15 weight gradient, bit 6 = strided conv_15 data gradient, bit 7 = strided conv_15 forward
+// bit 5 = conv_15 weight gradient, bit 6 = strided conv_15 data gradient, bit 7 = strided conv_15 forward,
+// bit 8 = strided conv_15 weight gradient
 inline bool tc_part(int bit) {
   static int v = -1;
-  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 255; }
+  if (v < 0) { const char* s = getenv("GNAS_TC_PART"); v = s ? atoi(s) : 511; }
   return (v >> bit) & 1;
 }
 #ifndef GNAS_EMUL
@@ -691,7 +692,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     auto pw_dx = [&](DxBatch& b) { return tc_pw_on(C) ? launch_conv_dx_tc(b, 1, c.st) : launch_dense_dx(1, 1, b, c.st); };
     auto conv_wg = [&](WgBatch& b, int stride) {
 #ifndef GNAS_EMUL
-      if (tc_enabled() && stride == 1 && tc_part(5) && tc::conv_wgrad_tc_supported(b)) return tc::launch_conv_wgrad_tc(b, c.st);
+      if (tc_enabled() && tc_part(stride == 1 ? 5 : 8) && tc::conv_wgrad_tc_supported(b, stride)) return tc::launch_conv_wgrad_tc(b, stride, c.st);
 #endif
       return launch_conv_wgrad(15, stride, 7, b, c.st);
     };

@@ -12,7 +12,11 @@
 namespace gnas {
 namespace tc {
 
-struct WgTcBatch { int n, B, rows_per_cta; WgJob j[kMaxDense]; };
+// Per-job tap geometry of the conv weight gradient: the kernel's local tap k (0..15) belongs to weight tap
+// tau0 + tstep * k (if k < ntaps), reads R at decimated position rs * pos + ro, and output position l pairs with
+// input position l + k - halo.  Stride-1 conv_15: {7, 0, 1, 15, 1, 0}; phase phi of a stride-S conv: see cell.cu.
+struct WgTap { int halo, tau0, tstep, ntaps, rs, ro; };
+struct WgTcBatch { int n, B, rows_per_cta; WgJob j[kMaxDense]; WgTap tap[kMaxDense]; };
 
 constexpr int kPwStages = 3;
 constexpr int kPwOp = 8 * 128 * 4;                 // floats of one operand half: [8 k-chunks][128 rows][4]
@@ -280,7 +284,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
   constexpr int RA = Cfg::RA, RB = Cfg::RB, TS = Cfg::TS, NG = Cfg::NG, CO = Cfg::CO, NB = Cfg::NB, BCH = Cfg::BCH, NST = Cfg::NST;
   constexpr int A_OP = Cfg::A_OP, B_OP = Cfg::B_OP, STAGE = Cfg::STAGE, NV = Cfg::NV;
   const WgJob& J = P.j[blockIdx.y];
-  const int L = J.Lo;
+  const WgTap TP = P.tap[blockIdx.y];
+  const int L = J.Lo, LR = J.Lin;                           // output positions (K), input row length
+  const int nguse = (TP.ntaps + TS - 1) / TS < NG ? (TP.ntaps + TS - 1) / TS : NG;   // tap groups that hold wanted taps
   const int spr = (L + RA - 1 + 31) / 32;                   // stages per batch row (A rows are shifted by up to RA - 1)
   const int bs = blockIdx.x * P.rows_per_cta, be = min(P.B, bs + P.rows_per_cta);
   if (bs >= be) return;
@@ -335,6 +341,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
           const uint64_t ah = a0 + so + (uint64_t)((ks * 2 * LBO_A) >> 4), al = ah + (uint64_t)((A_OP * 4) >> 4);
 #pragma unroll
           for (int a = 0; a < NG; ++a) {
+            if (a >= nguse) continue;
             const uint64_t bh = b0 + so + (uint64_t)(((ks * 2 + a * CO) * LBO_B) >> 4), bl = bh + (uint64_t)((B_OP * 4) >> 4);
             if constexpr (NV == 1) {
               const uint32_t acc = tmem_d + a * NB;
@@ -391,12 +398,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
           const int q = idx - NA;
           const int jc = q / NB, r = q - jc * NB;
           const int sbl = r / C, ch = r - sbl * C;
-          const int pos = p0 + 4 * jc + RA * (sb0 + sbl) - 7;
-          const float* rp = rb_ + (long long)ch * L + pos;
+          const int pos = p0 + 4 * jc + RA * (sb0 + sbl) - TP.halo;
+          const float* rp = rb_ + (long long)ch * LR + TP.ro;
           if (sbl < RB || C == 128) {             // C = 8: rows 8..15 are padding
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (pos + e >= 0 && pos + e < L) xv[i][e] = rp[e];
+              if (pos + e >= 0 && TP.rs * (pos + e) + TP.ro < LR) xv[i][e] = rp[(long long)TP.rs * (pos + e)];
           }
         }
       }
@@ -417,13 +424,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
         } else {
           const int q = idx - NA;
           const int jc = q / NB, r = q - jc * NB;
-          const int pos = p0 + 4 * jc + RA * (sb0 + r / C) - 7;
+          const int pos = p0 + 4 * jc + RA * (sb0 + r / C) - TP.halo;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float v = xv[i][e];
             if (tin == T_BN_RELU) v = (v - bpar[r]) * bpar[128 + r];
             if (tin == T_RELU || tin == T_BN_RELU) v = v > 0.f ? v : 0.f;
-            a[e] = (pos + e >= 0 && pos + e < L && (r / C < RB || C == 128)) ? v : 0.f;
+            a[e] = (pos + e >= 0 && TP.rs * (pos + e) + TP.ro < LR && (r / C < RB || C == 128)) ? v : 0.f;
           }
           dst = stage + 2 * A_OP + ((size_t)jc * NB + r) * 4;
         }
@@ -448,7 +455,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
     float* wrow = J.dw + (size_t)co * C * 15;
     if constexpr (NB >= 32) {
       constexpr int NBLK = NB / 32;
-      for (int u = (warp >> 2); u < NG * NBLK; u += 2) {
+      for (int u = (warp >> 2); u < nguse * NBLK; u += 2) {
         const int a = u / NBLK, blk = u - a * NBLK;
         float v[32];
         const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(a * NB + blk * 32);
@@ -464,8 +471,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
         for (int i = 0; i < 32; ++i) {
           const int col = blk * 32 + i;
           const int sbl = col / C, ci = col - sbl * C;
-          const int t = sa + RA * (sb0 + sbl) + TS * a;
-          if (t < 15) atomicAdd(wrow + (size_t)ci * 15 + t, v[i]);
+          const int t = sa + RA * (sb0 + sbl) + TS * a, tau = TP.tau0 + TP.tstep * t;
+          if (t < TP.ntaps && tau < 15) atomicAdd(wrow + (size_t)ci * 15 + tau, v[i]);
         }
       }
     } else if (warp < 4) {
@@ -480,8 +487,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
 #pragma unroll
         for (int vv = 0; vv < NV; ++vv) sum += v[(vv * NC + i) / 32][(vv * NC + i) % 32];
         const int a = i / NB, ci = i - a * NB;
-        const int t = sa + TS * a;
-        if (ci < C && t < 15) atomicAdd(wrow + (size_t)ci * 15 + t, sum);
+        const int t = sa + TS * a, tau = TP.tau0 + TP.tstep * t;
+        if (ci < C && t < TP.ntaps && tau < 15) atomicAdd(wrow + (size_t)ci * 15 + tau, sum);
       }
     }
   }
@@ -507,21 +514,33 @@ static void launch_conv_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* na
   prof_after(st);
 }
 
-// jobs must share (Cout = Cin = C, stride 1, Lo = Lin)
-static inline bool conv_wgrad_tc_supported(const WgBatch& b) {
+// jobs must share (Cout = Cin = C, Lo); stride 1: Lo = Lin
+static inline bool conv_wgrad_tc_supported(const WgBatch& b, int stride) {
   if (!wgrad_tc_channels(b.Cout)) return false;
+  if (stride > 1 && b.n * stride > kMaxDense) return false;
   for (int i = 0; i < b.n; ++i) {
     const WgJob& j = b.j[i];
-    if (j.Cin != b.Cout || j.Lo != j.Lin || j.Lo != b.j[0].Lo) return false;
+    if (j.Cin != b.Cout || (stride == 1 && j.Lo != j.Lin) || j.Lo != b.j[0].Lo) return false;
     if (!(j.tin == T_RELU || j.tin == T_BN_RELU || j.tin == T_NONE)) return false;
   }
   return true;
 }
 
-static int launch_conv_wgrad_tc(WgBatch& b, cudaStream_t st) {
+// stride S > 1: one job per input phase phi = 0..S-1 (x[S q + phi]): weight taps tau = (phi + 7) mod S + S k
+static int launch_conv_wgrad_tc(WgBatch& b, int stride, cudaStream_t st) {
   if (b.n == 0) return 0;
-  WgTcBatch t; t.n = b.n; t.B = b.B;
-  for (int i = 0; i < b.n; ++i) t.j[i] = b.j[i];
+  WgTcBatch t; t.n = 0; t.B = b.B;
+  for (int i = 0; i < b.n; ++i)
+    for (int phi = 0; phi < stride; ++phi) {
+      t.j[t.n] = b.j[i];
+      WgTap& tp = t.tap[t.n++];
+      if (stride == 1) { tp.halo = 7; tp.tau0 = 0; tp.tstep = 1; tp.ntaps = 15; tp.rs = 1; tp.ro = 0; }
+      else {
+        const int t0 = (phi + 7) % stride;
+        tp.halo = (7 + phi - t0) / stride; tp.tau0 = t0; tp.tstep = stride; tp.ntaps = (14 - t0) / stride + 1;
+        tp.rs = stride; tp.ro = phi;
+      }
+    }
   switch (b.Cout) {
     case 8: launch_conv_wgrad_tc_t<8>(t, st, "k_conv_wgrad_tc<8>"); break;
     case 16: launch_conv_wgrad_tc_t<16>(t, st, "k_conv_wgrad_tc<16>"); break;
