@@ -12,6 +12,7 @@
 // Backward: staged launches per (time step, node) -- elementwise/BN kernel + split-K GEMM against
 // Ws[i]^T -- and, off the critical path, one batched GEMM pass for dW0 / dWs over all time steps.
 #include "common.cuh"
+#include <cstdlib>
 #include "tc_common.cuh"
 #include "rhn_wgrad_tc.cuh"
 #include "../../include/gnas.h"
@@ -917,7 +918,9 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
   bp.tb = tb;
   const int eb = (H + 7) / 8;
   int ksplit = 1;                       // split K = 2H into CTAs of at most 4 chunks of 32 (all prefetched at once)
-  while ((2 * H) / ksplit > 4 * kGemmKC && (2 * H) % (ksplit * 2 * kGemmKC) == 0) ksplit *= 2;
+  static int kchunks = -1;
+  if (kchunks < 0) { const char* e = getenv("GNAS_RHN_KCH"); kchunks = e ? atoi(e) : 2; }   // 2 x 32 rows of K per CTA: 1024 CTAs for node 7, one round at 7 CTAs per SM (4: 512 CTAs, two rounds at 3 per SM)
+  while ((2 * H) / ksplit > kchunks * kGemmKC && (2 * H) % (ksplit * 2 * kGemmKC) == 0) ksplit *= 2;
   const int nch_g = (2 * H) / ksplit / kGemmKC;
   const size_t gsm = sizeof(float) * (size_t)nch_g * (kGemmKC * 64 + kGemmKC * BP);
 #ifndef GNAS_EMUL
