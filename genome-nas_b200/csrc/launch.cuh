@@ -171,21 +171,33 @@ static int launch_pw_wgrad(int S, WgBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
   const int Cin = b.j[0].Cin, Lo = b.j[0].Lo;
   for (int i = 1; i < b.n; ++i) if (b.j[i].Cin != Cin || b.j[i].Lo != Lo) { set_error("pw_wgrad: mixed shapes"); return GNAS_ERR_ARG; }
-  const int TC = pick_tc(b.Cout, Cin);
+  int TC = pick_tc(b.Cout, Cin);
   b.S = S; b.pad = 0;
-  b.COB = b.Cout < 16 * TC ? b.Cout : 16 * TC;
-  b.CIB = Cin < 16 * TC ? Cin : 16 * TC;
-  while ((b.COB / TC) * (b.CIB / TC) > kThreads) b.CIB /= 2;
-  if (b.Cout % b.COB || Cin % b.CIB || b.COB % TC || b.CIB % TC) { set_error("pw_wgrad: channel counts must tile"); return GNAS_ERR_SHAPE; }
-  const int cmax = b.COB > b.CIB ? b.COB : b.CIB;
-  int tl = 4096 / cmax;
-  tl = tl > 512 ? 512 : (tl < 64 ? 64 : tl);
-  b.TL = tl;
-  const int nblk = (b.Cout / b.COB) * (Cin / b.CIB);
-  const int tiles = b.B * cdiv(Lo, b.TL);
-  int tpc = (int)((long long)tiles * nblk * b.n / kWgradTargetCtas);
-  b.TPC = tpc < 1 ? 1 : tpc;
-  const int ny = cdiv(tiles, b.TPC);
+  int nblk = 1, ny = 1, tpc = 0;
+  auto configure = [&](int tc) -> bool {
+    b.COB = b.Cout < 16 * tc ? b.Cout : 16 * tc;
+    b.CIB = Cin < 16 * tc ? Cin : 16 * tc;
+    while ((b.COB / tc) * (b.CIB / tc) > kThreads) b.CIB /= 2;
+    if (b.Cout % b.COB || Cin % b.CIB || b.COB % tc || b.CIB % tc) return false;
+    const int cmax = b.COB > b.CIB ? b.COB : b.CIB;
+    int tl = 4096 / cmax;
+    tl = tl > 512 ? 512 : (tl < 64 ? 64 : tl);
+    b.TL = tl;
+    nblk = (b.Cout / b.COB) * (Cin / b.CIB);
+    const int tiles = b.B * cdiv(Lo, b.TL);
+    tpc = (int)((long long)tiles * nblk * b.n / kWgradTargetCtas);
+    b.TPC = tpc < 1 ? 1 : tpc;
+    ny = cdiv(tiles, b.TPC);
+    return true;
+  };
+  if (!configure(TC)) { set_error("pw_wgrad: channel counts must tile"); return GNAS_ERR_SHAPE; }
+  // Every CTA flushes its COB x CIB block with atomics once: with few jobs and wide blocks the position range is
+  // cut into many chunks and the flushes (ny * Cout * Cin atomics on the same addresses) dominate.  Smaller
+  // register tiles give more blocks, hence fewer, longer chunks.
+  while (tpc < 4 && TC > 1) {
+    if (!configure(TC / 2)) { configure(TC); break; }
+    TC /= 2;
+  }
   switch (TC) {
     case 8: launch_pw_wgrad_t<8>(b, nblk, ny, st); break;
     case 4: launch_pw_wgrad_t<4>(b, nblk, ny, st); break;
