@@ -506,7 +506,9 @@ static void launch_conv_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* na
   static bool prepared = false;
   if (!prepared) { cudaFuncSetAttribute(k_conv_wgrad_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem); prepared = true; }
   const int L = b.j[0].Lo, spr = (L + Cfg::RA - 1 + 31) / 32;
-  int rows = 10 / spr;                       // ~10 stages (= 40 k-steps) per accumulation chain
+  static int chain = -1;                     // stages per accumulation chain (GNAS_WG_CHAIN: A/B runs)
+  if (chain < 0) { const char* e = getenv("GNAS_WG_CHAIN"); chain = e ? atoi(e) : 10; }
+  int rows = chain / spr;                    // ~10 stages (= 40 k-steps) per accumulation chain
   rows = rows < 1 ? 1 : rows;
   b.rows_per_cta = rows;
   prof_before(name, "", st);
