@@ -24,7 +24,8 @@ PW = [False, False, False, False, True, True, True, True, False]
 cases = [(c + ([False] * 8 + [True],)) for c in cases] + [(2, 32, 250, 1, PW), (2, 64, 125, 1, PW), (3, 128, 42, 1, PW), (5, 128, 42, 3, ALL),
                                                         (2, 64, 125, 2, ALL), (3, 32, 250, 1, ALL), (2, 128, 130, 1, PW),
                                                         (3, 8, 1000, 1, ALL), (2, 16, 500, 1, ALL), (2, 8, 77, 1, ALL), (3, 16, 40, 2, ALL), (2, 16, 333, 1, [False] * 8 + [True]), (3, 16, 500, 1, PW), (5, 16, 50, 1, ALL),
-                                                        (2, 32, 250, 2, ALL), (3, 128, 125, 3, ALL), (2, 64, 77, 2, [False] * 8 + [True]), (5, 128, 41, 3, [False] * 8 + [True])]
+                                                        (2, 32, 250, 2, ALL), (3, 128, 125, 3, ALL), (2, 64, 77, 2, [False] * 8 + [True]), (5, 128, 41, 3, [False] * 8 + [True]),
+                                                        (1, 32, 1, 1, ALL), (70, 32, 3, 1, ALL), (2, 64, 1000, 1, ALL), (3, 128, 2, 3, ALL), (2, 64, 5, 2, ALL), (1, 16, 129, 1, ALL)]
 for B, C, L, S, sw in cases:
     torch.manual_seed(1)
     m = G.MixedOp(C, S, sw, 0.0)
