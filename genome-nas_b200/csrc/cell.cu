@@ -152,7 +152,7 @@ int launch_conv_dx_strided_tc(DxBatch& xb, int S, cudaStream_t st) {
 }
 void pack_tc(tc::TcPackBatch& pb, cudaStream_t st) {
   if (pb.n == 0) return;
-  GNAS_LAUNCH(tc::k_pack_tc, dim3(8, pb.n), dim3(256), 0, st, pb);
+  GNAS_LAUNCH(tc::k_pack_tc, dim3(32, pb.n), dim3(256), 0, st, pb);
   pb.n = 0;
 }
 #else
