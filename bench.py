@@ -139,6 +139,9 @@ def algorithmic_work(B):
     pw = sum(14 * 6 * 2 * B * C * C * Lo for C, _, Lo, _ in cell_geometry())                # 4 sep + 2 dil pointwise
     w["conv15_fwd_flops"] = conv15
     w["pw_fwd_flops"] = pw
+    # conv_15 convolutions that run on the tcgen05 kernels (C >= 16: all 28 per cell; strided first convs count at
+    # their output length), forward + data gradient
+    w["conv15_tc_flops"] = sum(2 * 14 * 2 * B * C * C * Lo * 15 for C, _, Lo, _ in cell_geometry() if C >= 16)
     w["mix_bytes"] = sum(4 * B * C * Lo * (sum(8 * (2 + i) for i in range(4)) + 4) for C, _, Lo, _ in cell_geometry())
     return w
 
@@ -349,6 +352,12 @@ def main():
             roofline = {"kernel": top, "bound": "hbm", "achieved": None, "peak": peaks.get("hbm_gbs", 6650.0),
                         "unit": "GB/s", "frac": None, "traffic": None, "launches_per_step": launches_top,
                         "ms_per_step": t_top}
+        # the tensor-core families next to it (algorithmic fp32 FLOPs; every multiply-add costs three TF32 MMAs)
+        tc_fl = {"conv15_tc(fwd+dx)": 4 * work["conv15_tc_flops"], "conv15_wgrad_tc": work["conv15_fwd_flops"],
+                 "rhn_wgrad_tc": flops["rhn_wgrad_tc"]}
+        if roofline is not None:
+            roofline["tensor_core_kernels"] = {k: {"ms_per_step": round(fam[k][1], 3), "tflops": round(v / (fam[k][1] / 1e3) / 1e12, 1)}
+                                               for k, v in tc_fl.items() if k in fam and fam[k][1] > 0}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
