@@ -97,6 +97,9 @@ class _FusedCellFunction(torch.autograd.Function):
     def backward(ctx, dout):
         lib = _lib.lib()
         runner, desc = ctx.runner, ctx.desc
+        if not desc.training:
+            raise RuntimeError("genome_nas_b200: backward through a cell evaluated in eval mode (running-statistics "
+                               "BatchNorm) is not implemented; evaluate under torch.no_grad() or call train()")
         s0, s1, weights, out, ws = ctx.saved_tensors
         has_pre = runner._has_pre
         dout = _lib.require(dout.contiguous(), "grad_output")
@@ -140,21 +143,30 @@ class _FusedBase(nn.Module):
             torch._foreach_add_(nbt, 1)
 
     def _draw_skip_masks(self, desc, like):
-        """nn.Dropout(p) behind the identity skips (P-DARTS; model_discCNN.py:60-61): masks are drawn here
-        with torch's generator for `like.device`, pre-scaled by 1/(1-p), and applied inside the kernels."""
-        p = float(self.p)
-        if not (p > 0 and desc.training):
+        """nn.Dropout(p) behind the identity skips (P-DARTS; model_discCNN.py:60-61).  Like the reference, an edge
+        has skip dropout only if its MixedOp was BUILT with p > 0 (Identity wrapped in nn.Sequential(Identity,
+        Dropout)); `update_p()` changes the rate of those wrappers and nothing else.  Masks are drawn with torch's
+        generator for `like.device`, pre-scaled by 1/(1-p), and applied inside the kernels."""
+        if not desc.training:
             return None, None
         masks, arr = [], (C.c_int64 * _lib.MAX_EDGES)()
         for e in range(desc.n_edges):
-            if desc.sw[e][3] and self._edge_stride(e) == 1:
+            arr[e] = 0
+            p = self._skip_dropout_p(e)
+            if p > 0 and desc.sw[e][3] and self._edge_stride(e) == 1:
                 m = torch.empty(desc.B, desc.C, desc.L_out, dtype=torch.float32, device=like.device)
                 m.bernoulli_(1.0 - p).div_(1.0 - p)
                 masks.append(m)
                 arr[e] = m.data_ptr()
-            else:
-                arr[e] = 0
-        return masks, arr
+        return (masks, arr) if masks else (None, None)
+
+
+def _skip_p_of(mixed):
+    """rate of the Dropout behind the identity skip of one MixedOp, 0 when the wrapper does not exist"""
+    op = getattr(mixed.m_ops, 'skip_connect', None)
+    if isinstance(op, nn.Sequential) and isinstance(op[0], Identity) and isinstance(op[1], nn.Dropout):
+        return float(op[1].p)
+    return 0.0
 
 
 class MixedOp(_FusedBase):
@@ -183,6 +195,9 @@ class MixedOp(_FusedBase):
 
     def _edge_stride(self, e):
         return self._stride
+
+    def _skip_dropout_p(self, e):
+        return _skip_p_of(self)
 
     def _descriptor(self, region, s0, s1, weights):
         B, Cc, L = s1.shape
@@ -245,6 +260,9 @@ class CNN_Cell_search(_FusedBase):
 
     def _edge_stride(self, e):
         return self.cell_ops[e]._stride
+
+    def _skip_dropout_p(self, e):
+        return _skip_p_of(self.cell_ops[e])
 
     def _descriptor(self, region, s0, s1, weights):
         B, c_pp, L_pp = s0.shape

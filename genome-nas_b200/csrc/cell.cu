@@ -1020,6 +1020,10 @@ extern "C" int gnas_cell_backward(const GnasCellDesc* d, const float* params, fl
       (d->has_pre && (!s0 || !ds0))) {
     set_error("cell_backward: null pointer"); return GNAS_ERR_ARG;
   }
+  if (!d->training) {   // the kernels differentiate batch-statistics BatchNorm only
+    set_error("cell_backward: the forward ran in eval mode (running statistics); its backward is not implemented");
+    return GNAS_ERR_UNSUPPORTED;
+  }
   Ctx c;
   c.d = d; make_plan(d, c.P);
   c.params = params; c.grads = grads; c.running = nullptr; c.s0 = s0; c.s1 = s1; c.mixw = mixw;

@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(kThreads) k_dense_bwd_dx(const __grid_constant
   const int ds_sz = KC * Wp, ws_sz = KC * KW * Cin;
   float* dsb = smem;                              // [2][KC][Wp]  dz tiles
   float* wsb = dsb + 2 * ds_sz;                   // [2][KC][KW][Cin]
-  float* ssum = wsb + 2 * ws_sz;                  // [2][Cin]
-  for (int i = tid; i < 2 * Cin; i += kThreads) ssum[i] = 0.f;
+  double* ssum = reinterpret_cast<double*>(wsb + 2 * ws_sz);   // [2][Cin], double: order-independent (see k_dense_fwd)
+  for (int i = tid; i < 2 * Cin; i += kThreads) ssum[i] = 0.0;
   float acc[TM][4];
 #pragma unroll
   for (int m = 0; m < TM; ++m)
@@ -315,15 +315,15 @@ __global__ void __launch_bounds__(kThreads) k_dense_bwd_dx(const __grid_constant
     if (J.omode == O_BNRELU_STORE) {
       if (pow2 && S == 1) {
         for (int o = width >> 1; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); qq += __shfl_xor_sync(0xffffffffu, qq, o); }
-        if (active && (q & (width - 1)) == 0) { atomicAdd(&ssum[ci], s); atomicAdd(&ssum[Cin + ci], qq); }
+        if (active && (q & (width - 1)) == 0) { atomicAdd(&ssum[ci], (double)s); atomicAdd(&ssum[Cin + ci], (double)qq); }
       } else if (active) {
-        atomicAdd(&ssum[ci], s); atomicAdd(&ssum[Cin + ci], qq);
+        atomicAdd(&ssum[ci], (double)s); atomicAdd(&ssum[Cin + ci], (double)qq);
       }
     }
   }
   if (J.omode == O_BNRELU_STORE) {
     __syncthreads();
-    for (int i = tid; i < 2 * Cin; i += kThreads) atomicAdd(&J.bacc[i], (double)ssum[i]);
+    for (int i = tid; i < 2 * Cin; i += kThreads) atomicAdd(&J.bacc[i], ssum[i]);
   }
 }
 

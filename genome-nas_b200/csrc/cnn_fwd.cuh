@@ -69,8 +69,10 @@ __global__ void __launch_bounds__(kThreads) k_dense_fwd(const __grid_constant__ 
   const int xs_sz = KC * Wp, ws_sz = KC * KW * Cout;
   float* xsb = smem;                            // [2][KC][Wp]
   float* wsb = xsb + 2 * xs_sz;                 // [2][KC][KW][Cout]
-  float* ssum = wsb + 2 * ws_sz;                // [2][Cout]
-  for (int i = tid; i < 2 * Cout; i += kThreads) ssum[i] = 0.f;
+  // per-CTA statistics are summed in double from the per-warp partials on: the float result no longer depends
+  // on the order in which the warps arrive (deterministic BN statistics, hence reproducible ReLU decisions)
+  double* ssum = reinterpret_cast<double*>(wsb + 2 * ws_sz);   // [2][Cout]
+  for (int i = tid; i < 2 * Cout; i += kThreads) ssum[i] = 0.0;
   float acc[TM][4];
 #pragma unroll
   for (int m = 0; m < TM; ++m)
@@ -183,15 +185,15 @@ __global__ void __launch_bounds__(kThreads) k_dense_fwd(const __grid_constant__ 
     if (J.acc != nullptr) {
       if (pow2) {
         for (int o = width >> 1; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-        if (active && (lg & (width - 1)) == 0) { atomicAdd(&ssum[co], s); atomicAdd(&ssum[Cout + co], q); }
+        if (active && (lg & (width - 1)) == 0) { atomicAdd(&ssum[co], (double)s); atomicAdd(&ssum[Cout + co], (double)q); }
       } else if (active) {
-        atomicAdd(&ssum[co], s); atomicAdd(&ssum[Cout + co], q);
+        atomicAdd(&ssum[co], (double)s); atomicAdd(&ssum[Cout + co], (double)q);
       }
     }
   }
   if (J.acc != nullptr) {
     __syncthreads();
-    for (int i = tid; i < 2 * Cout; i += kThreads) atomicAdd(&J.acc[i], (double)ssum[i]);
+    for (int i = tid; i < 2 * Cout; i += kThreads) atomicAdd(&J.acc[i], ssum[i]);
   }
 }
 

@@ -103,6 +103,18 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+#ifndef GNAS_EMUL
+// Kernel attributes (dynamic shared-memory opt-in) are per DEVICE: one table entry per ordinal, so that a process
+// which drives several GPUs prepares every kernel on each of them (returns true when the attribute must be set).
+constexpr int kMaxDevices = 64;
+static inline bool need_prepare(int* table, int want) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return true;
+  if (want > table[dev]) { table[dev] = want; return true; }
+  return false;
+}
+#endif
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return cdiv(a, b) * b; }

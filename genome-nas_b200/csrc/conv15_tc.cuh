@@ -123,7 +123,7 @@ template <int C, int KW> struct TcCfg {
   static constexpr int W_UNIT = 2 * C * 4;                 // floats of one unit (2 core-matrix columns x C rows), hi or lo
   static constexpr int W_CHUNK = TT * W_UNIT;
   static constexpr int A_HALF = (C / 4) * ROWS * 4;        // floats of A_hi (= A_lo)
-  static constexpr size_t smem = sizeof(float) * (size_t)(2 * A_HALF + NST * 2 * W_CHUNK + 6 * C) + 128;
+  static constexpr size_t smem = sizeof(float) * (size_t)(2 * A_HALF + NST * 2 * W_CHUNK + 8 * C) + 128;
   static_assert(NU % TT == 0, "chunks must tile the units");
 };
 
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
   float* A_hi = reinterpret_cast<float*>(tc_smem_raw);
   float* A_lo = A_hi + A_HALF;
   float* Wb = A_lo + A_HALF;                                // [NST][hi | lo][W_CHUNK]
-  float* ssum = Wb + NST * 2 * W_CHUNK;                     // [2][C]
-  float* sp = ssum + 2 * C;                                 // [3][C] input-transform parameters
+  double* ssum = reinterpret_cast<double*>(Wb + NST * 2 * W_CHUNK);   // [2][C] in double: order-independent statistics
+  float* sp = reinterpret_cast<float*>(ssum + 2 * C);       // [3][C] input-transform parameters
   float* smean = sp + 3 * C;                                // [C] mean of the inner BN (O_BNRELU_STORE)
   __shared__ __align__(8) uint64_t bar_full[NST], bar_empty[NST], bar_a[G], bar_done;
   __shared__ uint32_t tmem_base_s;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 2 * C; i += kTcThreads) ssum[i] = 0.f;
+  for (int i = tid; i < 2 * C; i += kTcThreads) ssum[i] = 0.0;
   {
     const int np = J.tin == T_BN_RELU ? 2 * C : (J.tin < 0 && J.x2 ? 3 * C : 0);
     for (int i = tid; i < np; i += kTcThreads) sp[i] = J.in_stat[i];
@@ -395,8 +395,8 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
         if (stats && omode != O_RELU_ACC) {
           const float s = warp_transpose_sum(v, lane), qq = warp_transpose_sum(q, lane);
           if (lane < NV) {
-            atomicAdd(&ssum[c0 + lane], s);
-            atomicAdd(&ssum[C + c0 + lane], qq);
+            atomicAdd(&ssum[c0 + lane], (double)s);
+            atomicAdd(&ssum[C + c0 + lane], (double)qq);
           }
         }
       }
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(kTcThreads, C == 128 ? 1 : 2) k_conv_tc(const 
   __syncthreads();
   TC_MARK(5);
   if (J.acc != nullptr)
-    for (int i = tid; i < 2 * C; i += kTcThreads) atomicAdd(&J.acc[i], (double)ssum[i]);
+    for (int i = tid; i < 2 * C; i += kTcThreads) atomicAdd(&J.acc[i], ssum[i]);
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TM_COLS) : "memory");
@@ -419,8 +419,8 @@ static inline bool tc_supported(int C) { return C == 16 || C == 32 || C == 64 ||
 template <int C, int KW>
 static void launch_conv_tc_t(const TcBatch& b, dim3 grid, cudaStream_t st, const char* name) {
   const size_t smem = TcCfg<C, KW>::smem;
-  static bool prepared = false;
-  if (!prepared) { cudaFuncSetAttribute(k_conv_tc<C, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); prepared = true; }
+  static int prepared[kMaxDevices] = {0};
+  if (need_prepare(prepared, (int)smem)) cudaFuncSetAttribute(k_conv_tc<C, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   prof_before(name, "", st);
   k_conv_tc<C, KW><<<grid, dim3(kTcThreads), smem, st>>>(b);
   prof_after(st);

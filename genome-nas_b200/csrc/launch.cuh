@@ -12,11 +12,9 @@ namespace gnas {
 #else
 #define GNAS_PREP_SMEM(kernel, bytes)                                                       \
   do {                                                                                      \
-    static int prepared_bytes = 0;                                                          \
-    if ((int)(bytes) > prepared_bytes) {                                                    \
+    static int prepared_bytes[kMaxDevices] = {0};                                           \
+    if (need_prepare(prepared_bytes, (int)(bytes)))                                         \
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
-      prepared_bytes = (int)(bytes);                                                        \
-    }                                                                                       \
   } while (0)
 #endif
 
@@ -47,7 +45,7 @@ static void launch_dense_fwd_t(DenseBatch& b, int maxLout, cudaStream_t st) {
   int cins[kMaxDense];
   for (int i = 0; i < b.n; ++i) cins[i] = b.j[i].Cin;
   b.KC = choose_kc(KW, cins, b.n, b.Cout, Wp);
-  const size_t smem = sizeof(float) * (2 * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cout) + 2 * b.Cout);
+  const size_t smem = sizeof(float) * (2 * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cout) + 4 * b.Cout);
   GNAS_PREP_SMEM((k_dense_fwd<KW, S, TM>), smem);
   dim3 grid(cdiv(maxLout, b.TL), b.B, b.n);
   GNAS_LAUNCH((k_dense_fwd<KW, S, TM>), grid, dim3(kThreads), smem, st, b);
@@ -120,7 +118,7 @@ static void launch_dense_dx_t(DxBatch& b, int maxLin, cudaStream_t st) {
   int couts[kMaxDense];
   for (int i = 0; i < b.n; ++i) couts[i] = b.j[i].Cout;
   b.KC = choose_kc(KW, couts, b.n, b.Cin, Wp);
-  const size_t smem = sizeof(float) * (2 * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cin) + 2 * b.Cin);
+  const size_t smem = sizeof(float) * (2 * ((size_t)b.KC * Wp + (size_t)b.KC * KW * b.Cin) + 4 * b.Cin);
   GNAS_PREP_SMEM((k_dense_bwd_dx<KW, S, TM>), smem);
   dim3 grid(cdiv(maxLin, 4 * S * b.nq), b.B, b.n);
   GNAS_LAUNCH((k_dense_bwd_dx<KW, S, TM>), grid, dim3(kThreads), smem, st, b);

@@ -868,11 +868,10 @@ extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const floa
   GNAS_LAUNCH_COOP(k_rhn_forward, dim3(grid), dim3(kRhnThreads), smem, st, f);
 #else
   {
-    static size_t prepared = 0;
-    if (smem > prepared) {
+    static int prepared[kMaxDevices] = {0};
+    if (need_prepare(prepared, (int)smem)) {
       cudaError_t e = cudaFuncSetAttribute(k_rhn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("rhn_forward: shared memory request rejected"); return (int)e; }
-      prepared = smem;
     }
     int dev = 0, nsm = 0, per_sm = 0;
     cudaGetDevice(&dev);
@@ -899,6 +898,10 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
   if (!W0 || !Ws || !probs || !dout || !ws || !scratch || !dx || !dh0 || !dprobs || (need_wgrad && (!dW0 || !dWs))) {
     set_error("rhn_backward: null pointer"); return GNAS_ERR_ARG;
   }
+  if (!d->training) {   // the kernels differentiate batch-statistics BatchNorm only
+    set_error("rhn_backward: the forward ran in eval mode (running statistics); its backward is not implemented");
+    return GNAS_ERR_UNSUPPORTED;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   RhnPlan p = rhn_plan(d);
   const int H = d->H, BP = p.BP, B = d->B, T = d->T;
@@ -924,8 +927,8 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
   const int nch_g = (2 * H) / ksplit / kGemmKC;
   const size_t gsm = sizeof(float) * (size_t)nch_g * (kGemmKC * 64 + kGemmKC * BP);
 #ifndef GNAS_EMUL
-  { static size_t prepared = 0;
-    if (gsm > prepared) { cudaFuncSetAttribute(k_rhn_bwd_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm); prepared = gsm; } }
+  { static int prepared[kMaxDevices] = {0};
+    if (need_prepare(prepared, (int)gsm)) cudaFuncSetAttribute(k_rhn_bwd_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm); }
 #endif
   if (nch_g > 4 || nch_g < 1) { set_error("rhn_backward: unsupported hidden size for the GEMM split"); return GNAS_ERR_UNSUPPORTED; }
   for (int t = T - 1; t >= 0; --t) {

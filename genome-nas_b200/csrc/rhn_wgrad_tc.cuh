@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_rhn_wgrad_tc(const __grid_con
 }
 
 static void launch_rhn_wgrad_tc(RhnWgTc& w, cudaStream_t st) {
-  static bool prepared = false;
-  if (!prepared) { cudaFuncSetAttribute(k_rhn_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem); prepared = true; }
+  static int prepared[kMaxDevices] = {0};
+  if (need_prepare(prepared, (int)kWgSmem)) cudaFuncSetAttribute(k_rhn_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgSmem);
   const int H = w.H;
   w.is_w0 = 0; w.tsplit = 1;
   prof_before("k_rhn_wgrad_tc", "", st);

@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pw_wgrad_tc(const __grid_cons
 
 template <int C>
 static void launch_pw_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* name) {
-  static bool prepared = false;
-  if (!prepared) { cudaFuncSetAttribute(k_pw_wgrad_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPwSmem); prepared = true; }
+  static int prepared[kMaxDevices] = {0};
+  if (need_prepare(prepared, (int)kPwSmem)) cudaFuncSetAttribute(k_pw_wgrad_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPwSmem);
   const int groups = cdiv(b.n, 128 / C);
   int ksplit = cdiv(2 * 148, groups);
   ksplit = ksplit > b.B ? b.B : (ksplit < 1 ? 1 : ksplit);
@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_conv_wgrad_tc(const __grid_co
 template <int C>
 static void launch_conv_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* name) {
   using Cfg = CwCfg<C>;
-  static bool prepared = false;
-  if (!prepared) { cudaFuncSetAttribute(k_conv_wgrad_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem); prepared = true; }
+  static int prepared[kMaxDevices] = {0};
+  if (need_prepare(prepared, (int)Cfg::smem)) cudaFuncSetAttribute(k_conv_wgrad_tc<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem);
   const int L = b.j[0].Lo, spr = (L + Cfg::RA - 1 + 31) / 32;
   static int chain = -1;                     // stages per accumulation chain (GNAS_WG_CHAIN: A/B runs)
   if (chain < 0) { const char* e = getenv("GNAS_WG_CHAIN"); chain = e ? atoi(e) : 10; }

@@ -51,7 +51,7 @@ class _StemFunction(torch.autograd.Function):
         _lib.LAUNCHES += 1
         if training:
             bn.num_batches_tracked += 1
-        ctx.stem, ctx.dims, ctx.bwd_floats = stem, (B, C0, L), bwd.value
+        ctx.stem, ctx.dims, ctx.bwd_floats, ctx.training = stem, (B, C0, L), bwd.value, training
         ctx.need_wgrad = bool(getattr(stem, "_wgrad_enabled", True))
         ctx.save_for_backward(x, ws)
         return out
@@ -60,6 +60,9 @@ class _StemFunction(torch.autograd.Function):
     def backward(ctx, dout):
         if not ctx.need_wgrad:
             return None, None, None
+        if not ctx.training:
+            raise RuntimeError("genome_nas_b200: backward through the stem evaluated in eval mode (running-statistics "
+                               "BatchNorm) is not implemented; evaluate under torch.no_grad() or call train()")
         lib = _lib.lib()
         stem = ctx.stem
         x, ws = ctx.saved_tensors
@@ -146,7 +149,6 @@ class RNNModel(nn.Module):
             cell._wgrad_enabled = enabled
         for rnn in self.rnns:
             rnn._wgrad_enabled = enabled
-        self._head_wgrad = enabled
 
     @staticmethod
     def _softmax_alpha(alpha):

@@ -65,6 +65,9 @@ class _RhnFunction(torch.autograd.Function):
     def backward(ctx, dout):
         lib = _lib.lib()
         mod, desc = ctx.mod, ctx.desc
+        if not desc.training:
+            raise RuntimeError("genome_nas_b200: backward through the RHN layer evaluated in eval mode (running-"
+                               "statistics BatchNorm) is not implemented; evaluate under torch.no_grad() or call train()")
         x, h0, probs, ws = ctx.saved_tensors
         x_mask, h_mask = ctx.masks
         dout = _lib.require(dout.contiguous(), "grad_output")
@@ -119,9 +122,10 @@ class DARTSCellSearch(nn.Module):
         for r, row in enumerate(self.switch_rnn):
             for k, on in enumerate(row):
                 d.sw[r][k] = 1 if on else 0
-        n_rows = sum(1 for row in self.switch_rnn if any(row))
-        if probs.shape[0] < n_rows or any(sum(row) > d.n_prims for row in self.switch_rnn):
-            raise RuntimeError("RHN: probability matrix does not match switch_rnn")
+        # the backward kernel writes 36 * n_prims gradient entries: the matrix must be exactly [36, n_prims]
+        # (DARTS / P-DARTS / CWP-DARTS never disable a whole RNN edge)
+        if tuple(probs.shape) != (36, d.n_prims) or any(not any(row) or sum(row) > d.n_prims for row in self.switch_rnn):
+            raise RuntimeError(f"RHN: probability matrix must be [36, n_prims] and match switch_rnn, got {tuple(probs.shape)}")
         return d
 
     def forward(self, inputs, hidden):

@@ -64,14 +64,10 @@ def check_forward_backward(g, device, monkeypatch):
         if ref < 1e-12 * total:
             continue
         # per-tensor rel-L2 against fp64, graded against the reference's own fp32 run: the north
-        # star's 1e-3, or four times the error the reference itself makes on that tensor.  These gradients are
-        # chaotic at the 1e-3 level for ANY fp32 implementation: one ReLU / max-pool decision that sits on a
-        # rounding knife edge in a late layer (head ReLU: 64 x 925 units, cell 5: 64 x 128 x 42) moves every
-        # upstream gradient by ~1/sqrt(N) = 2-4e-3, and which side it falls on depends on the float-atomic
-        # summation order of the BN statistics.  Measured over repeated runs (tools/full_grad_err.py): error /
-        # ref32_err is 0.4-1.2 typically and 3.3 when one such decision flips; the op-level tests pin the
-        # arithmetic itself to 1e-6..1e-5 of fp64.
-        lim = max(1e-3, 4.0 * r32[n])
+        # star's 1e-3, or 1.5x the error the reference itself makes on that tensor.  BN statistics are summed in
+        # double from the per-warp partials on, so the forward pass (and with it every ReLU / max-pool decision)
+        # is reproducible run to run.
+        lim = max(1e-3, 1.5 * r32[n])
         if n in g["grad64"]:
             score[n] = relerr(p.grad, g["grad64"][n]) / lim
         else:
@@ -79,14 +75,8 @@ def check_forward_backward(g, device, monkeypatch):
             dot = float((gd.flatten() * probe_vec(i, gd.numel())).sum())
             # <g, r> with r ~ N(0, I): |error| <~ ||g - g_ref|| up to a chi-distributed factor
             score[n] = max(abs(float(gd.norm()) - ref) / (lim * ref), abs(dot - g["grad_dot64"][n]) / (5 * lim * ref))
-    # Every tensor within its limit -- except that the parameters of an edge or two may exceed it by a bounded
-    # factor: when one mask element of an edge flips (its pre-activation lies within rounding of the threshold; seen
-    # in about one run out of three for cells.4.cell_ops.9), all ~13-20 gradient tensors of that edge move together,
-    # the small ill-conditioned ones (a 64 x 15 depthwise filter whose norm is 1e-3 of its neighbours') by up to
-    # 1.3x their limit.
     over = {n: v for n, v in score.items() if v >= 1.0}
-    assert len(over) <= max(2, len(score) // 40), over
-    assert all(v < 5.0 for v in over.values()), over
+    assert not over, over
     dg = dict(m.named_parameters())["decoder.weight"].grad.detach().double().cpu()
     assert relerr(dg @ g["decoder_proj_vec"].double(), g["decoder_grad_proj64"]) < 2e-3
     return m

@@ -76,7 +76,7 @@ def test_rhn_wide_hidden_matches_oracle(backend, monkeypatch, nhid, B, T):
     """Hidden sizes that are multiples of 128 with batches that are multiples of 32 take the tcgen05 weight-gradient
     kernel on the GPU (rhn_wgrad_tc.cuh); the fp64 oracle (pinned to the reference by tests/golden/rhn.pt) is the
     checker."""
-    if backend != "cuda" and B > 32:
+    if backend.type != "cuda" and B > 32:
         pytest.skip("emulator: one wide case is enough")
     torch.manual_seed(5)
     switch = [[True] * 5 for _ in range(36)]
