@@ -37,6 +37,7 @@ _SIGS = {
     "gnas_kernel_launches": (C.c_int64, []),
     "gnas_profile_enable": (C.c_int, [C.c_int]),
     "gnas_profile_report": (C.c_int64, [C.c_char_p, C.c_int64]),
+    "gnas_profile_event_overhead_ms": (C.c_double, [C.c_int, _P]),
     "gnas_cell_workspace": (C.c_int, [C.POINTER(CellDesc), _I64P, _I64P]),
     "gnas_cell_forward": (C.c_int, [C.POINTER(CellDesc), _P, _P, _P, _P, _P, _I64P, _P, _P, _P]),
     "gnas_cell_backward": (C.c_int, [C.POINTER(CellDesc), _P, _P, _P, _P, _P, _I64P, _P, _P, _P, _P, _P, _P, _P,
@@ -51,7 +52,7 @@ _SIGS = {
     "gnas_grad_sumsq": (C.c_int, [_P, C.c_int64, _P, _P]),
     "gnas_sgd_step": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P, C.c_float, _P]),
     "gnas_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                 C.c_int, _P, _P]),
+                                 C.c_int, _P, _P, C.c_float, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -52,7 +52,13 @@ static __global__ void k_inc_step(int* step) { if (threadIdx.x == 0 && blockIdx.
 static __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g,
                                                      float* __restrict__ m, float* __restrict__ v, long long n,
                                                      float lr, float wd, float b1, float b2, float eps,
-                                                     float bc1, float bc2_sqrt, const int* step_dev) {
+                                                     float bc1, float bc2_sqrt, const int* step_dev,
+                                                     const double* sumsq, float clip) {
+  float coef = 1.f;          // clip_grad_norm_ over the architecture parameters (train_and_validate.py:97)
+  if (sumsq != nullptr) {
+    const float c = clip / ((float)sqrt(*sumsq) + 1e-6f);
+    coef = c < 1.f ? c : 1.f;
+  }
   if (step_dev != nullptr) {   // step counter lives on the device so that a captured CUDA graph stays valid
     const float t = (float)*step_dev;
     bc1 = 1.f - powf(b1, t);
@@ -60,7 +66,7 @@ static __global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, cons
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float pv = p[i];
-    const float gv = fmaf(wd, pv, g[i]);
+    const float gv = fmaf(wd, pv, coef * g[i]);
     const float mv = b1 * m[i] + (1.f - b1) * gv;
     const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
     m[i] = mv; v[i] = vv;
@@ -95,13 +101,14 @@ extern "C" int gnas_sgd_step(float* p, const float* g, float* mom, int64_t n, fl
 }
 
 extern "C" int gnas_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float wd,
-                              float beta1, float beta2, float eps, int step, int* step_dev, void* stream) {
+                              float beta1, float beta2, float eps, int step, int* step_dev,
+                              const double* sumsq, float clip, void* stream) {
   if (!p || !g || !m || !v || n < 0 || (step < 1 && !step_dev)) { set_error("adam_step: bad argument"); return GNAS_ERR_ARG; }
   if (n == 0) return 0;
   const float bc1 = 1.f - powf(beta1, (float)(step < 1 ? 1 : step));
   const float bc2 = sqrtf(1.f - powf(beta2, (float)(step < 1 ? 1 : step)));
   if (step_dev) GNAS_LAUNCH(k_inc_step, dim3(1), dim3(32), 0, (cudaStream_t)stream, step_dev);
   GNAS_LAUNCH(k_adam, dim3(blocks_for(n)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (long long)n, lr, wd,
-              beta1, beta2, eps, bc1, bc2, (const int*)step_dev);
+              beta1, beta2, eps, bc1, bc2, (const int*)step_dev, sumsq, clip);
   return check_launch("gnas_adam_step");
 }

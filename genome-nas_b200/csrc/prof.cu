@@ -1,6 +1,7 @@
 // Launch counter and optional per-kernel CUDA-event timing (used by bench.py for the roofline line).
 #include "common.cuh"
 #include "../../include/gnas.h"
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -66,6 +67,29 @@ using namespace gnas;
 extern "C" int64_t gnas_kernel_launches(void) { return g_launches; }
 
 extern "C" int gnas_profile_enable(int on) { g_enabled = on != 0; return 0; }
+
+// Median elapsed time (ms) of `n` EMPTY event pairs recorded back to back on `stream`: what an event pair reads
+// when nothing runs between its two records.  bench.py subtracts it, measured live in the same process, from
+// every bracketed launch (it replaces the round-1 calibration constant).
+extern "C" double gnas_profile_event_overhead_ms(int n, void* stream) {
+#ifndef GNAS_EMUL
+  if (n < 1) n = 1;
+  if (n > 4096) n = 4096;
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev(2 * (size_t)n);
+  for (auto& e : ev) cudaEventCreate(&e);
+  for (int i = 0; i < n; ++i) { cudaEventRecord(ev[2 * i], st); cudaEventRecord(ev[2 * i + 1], st); }
+  cudaStreamSynchronize(st);
+  std::vector<float> t((size_t)n, 0.f);
+  for (int i = 0; i < n; ++i) cudaEventElapsedTime(&t[i], ev[2 * i], ev[2 * i + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  std::sort(t.begin(), t.end());
+  return (double)t[(size_t)n / 2];
+#else
+  (void)n; (void)stream;
+  return 0.0;
+#endif
+}
 
 extern "C" int64_t gnas_profile_report(char* buf, int64_t cap) {
   std::string out;

@@ -27,6 +27,10 @@ class Hyper:
     arch_wd = 1e-3
     adam_betas = (0.9, 0.999)
     adam_eps = 1e-8
+    # P-DARTS / CWP-DARTS inline alpha step (train_and_validate.py:87-101, train_genomicPDARTS.py:300-301):
+    # Adam(lr 6e-4, betas (0.5, 0.999), wd 1e-3) after clip_grad_norm_(arch_parameters, clip).  None = Architect
+    # first-order step (no clipping of the alpha gradients).
+    arch_clip = None
 
 
 def tar_loss(rnn_h, beta):
@@ -51,8 +55,10 @@ class SearchStep:
         self.adam_m = torch.zeros(self.n_alpha, dtype=torch.float32, device=dev)
         self.adam_v = torch.zeros(self.n_alpha, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.sumsq_a = torch.zeros(1, dtype=torch.float64, device=dev)
         self.t_adam = torch.zeros(1, dtype=torch.int32, device=dev)     # device-side so CUDA graphs stay valid
         self.graph = None
+        self.mask_source = None     # optional callable(i, B, H, keep) -> [B, H] CPU mask (tests replay recorded masks)
 
     def _refresh(self):
         r = self.model.flat_region()
@@ -85,9 +91,15 @@ class SearchStep:
         """Adam on the three alpha tensors (architect.py:42,66)."""
         lib, h = _lib.lib(), self.h
         flat, g = self._refresh()
+        st = _lib.stream_ptr(flat)
+        sumsq, clip = None, 0.0
+        if getattr(h, "arch_clip", None) is not None:
+            self.sumsq_a.zero_()
+            _lib.check(lib.gnas_grad_sumsq(_lib.ptr(g), self.n_alpha, _lib.ptr(self.sumsq_a), st), "grad_sumsq")
+            sumsq, clip = self.sumsq_a, float(h.arch_clip)
         _lib.check(lib.gnas_adam_step(_lib.ptr(flat), _lib.ptr(g), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v),
                                       self.n_alpha, h.arch_lr, h.arch_wd, h.adam_betas[0], h.adam_betas[1], h.adam_eps,
-                                      0, _lib.ptr(self.t_adam), _lib.stream_ptr(flat)), "adam_step")
+                                      0, _lib.ptr(self.t_adam), _lib.ptr(sumsq), clip, st), "adam_step")
         _lib.LAUNCHES += 1
 
     def alpha_step(self, x_valid, y_valid):
@@ -172,7 +184,8 @@ class SearchStep:
         rnn = self.model.rnns[0]
         B, H = self._static_masks[0].shape
         for i, keep in enumerate((1. - rnn.dropoutx, 1. - rnn.dropouth) * 2):
-            self._mask_host[i].copy_(torch.floor(torch.rand(B, H) + keep) / keep)
+            m = self.mask_source(i, B, H, keep) if self.mask_source is not None else torch.floor(torch.rand(B, H) + keep) / keep
+            self._mask_host[i].copy_(m)
             self._static_masks[i].copy_(self._mask_host[i], non_blocking=True)
 
     def capture(self, x_train, y_train, x_valid, y_valid, warmup=2):

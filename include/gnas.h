@@ -43,6 +43,8 @@ int64_t gnas_kernel_launches(void);
  * (returns bytes written, <0 if cap is too small) and clears the records. */
 int gnas_profile_enable(int on);
 int64_t gnas_profile_report(char* buf_host, int64_t cap);
+/* median elapsed time (ms) of n empty event pairs on `stream`: the bracketing overhead, measured live */
+double gnas_profile_event_overhead_ms(int n, void* stream);
 
 /* ---- CNN search cell: darts_tools/model_discCNN.py:96-201 (CNN_Cell_search) with its
  * MixedOps (:46-93) and the operator zoo generalNAS_tools/operations_14_9.py:17-300.
@@ -131,9 +133,12 @@ int gnas_grad_sumsq(const float* g, int64_t n, double* out, void* stream);
 int gnas_sgd_step(float* p, const float* g, float* mom, int64_t n, float lr, float wd,
                   float momentum, int first_step, const double* sumsq, float clip, void* stream);
 /* step_dev (optional, device int): when given it is incremented and used for the bias correction instead of
- * `step`, so the call can be replayed from a CUDA graph. */
+ * `step`, so the call can be replayed from a CUDA graph.  sumsq (optional, device double = sum g^2 from
+ * gnas_grad_sumsq): gradients are scaled by min(1, clip/(sqrt(sumsq)+1e-6)) first -- the P-DARTS inline
+ * alpha step clips the architecture gradients (train_and_validate.py:87-101). */
 int gnas_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float wd,
-                   float beta1, float beta2, float eps, int step, int* step_dev, void* stream);
+                   float beta1, float beta2, float eps, int step, int* step_dev,
+                   const double* sumsq, float clip, void* stream);
 
 #ifdef __cplusplus
 }

@@ -379,6 +379,14 @@ class Hyper:
     beta: float = 1e-3
     arch_lr: float = 3e-3
     arch_wd: float = 1e-3
+    # P-DARTS / CWP-DARTS inline alpha step (train_and_validate.py:87-101, train_genomicPDARTS.py:300-301):
+    # Adam(6e-4, betas (0.5, 0.999), wd 1e-3) after clip_grad_norm_(arch_parameters, clip); None = Architect
+    adam_betas: Tuple[float, float] = (0.9, 0.999)
+    arch_clip: Optional[float] = None
+
+
+def pdarts_hyper() -> "Hyper":
+    return Hyper(arch_lr=6e-4, adam_betas=(0.5, 0.999), arch_clip=0.25)
 
 
 def adam_update(p, g, state, lr, wd, b1=0.9, b2=0.999, eps=1e-8):
@@ -395,7 +403,8 @@ def adam_update(p, g, state, lr, wd, b1=0.9, b2=0.999, eps=1e-8):
 
 def search_step(P, cfg, hyper: Hyper, x_train, y_train, x_valid, y_valid, opt_state,
                 masks_valid=(None, None), masks_train=(None, None)):
-    """One iteration of train() with train_arch=True, pdarts=False, unrolled=False.
+    """One iteration of train() with train_arch=True, unrolled=False; pdarts=False (Architect) or, with
+    hyper.arch_clip set, pdarts=True (inline clipped Adam, train_and_validate.py:87-101).
     train_and_validate.py:55-152 + architect.py:55-72.  P holds detached tensors;
     returns the updated dictionary and a dict of observables."""
     obs = {}
@@ -408,8 +417,13 @@ def search_step(P, cfg, hyper: Hyper, x_train, y_train, x_valid, y_valid, opt_st
     g = grads_of(loss_a, Q, list(arch))
     P = {k: v.detach() for k, v in Q.items()}
     rec.apply(P)
+    if hyper.arch_clip is not None:      # nn.utils.clip_grad_norm_(model.arch_parameters(), clip)  (:97)
+        tot_a = torch.sqrt(sum((g[n].double() ** 2).sum() for n in arch)).to(loss_a.dtype)
+        coef_a = torch.clamp(hyper.arch_clip / (tot_a + 1e-6), max=1.0)
+        g = {n: g[n] * coef_a for n in arch}
     for n in arch:
-        P[n] = adam_update(P[n], g[n], opt_state.setdefault("adam_" + n, {}), hyper.arch_lr, hyper.arch_wd)
+        P[n] = adam_update(P[n], g[n], opt_state.setdefault("adam_" + n, {}), hyper.arch_lr, hyper.arch_wd,
+                           hyper.adam_betas[0], hyper.adam_betas[1])
     obs["loss_valid"] = loss_a.detach()
     obs["alpha_grads"] = {n: g[n].detach() for n in arch}
     # ---- weight step: fwd+bwd with TAR on the training batch, global clip, SGD

@@ -281,7 +281,7 @@ class _Args:
     arch_wdecay = 1e-3
 
 
-def ref_search_step(m, hyper, xt, yt, xv, yv, seed):
+def ref_search_step(m, hyper, xt, yt, xv, yv, seed, pdarts=False):
     """The reference's own train() for exactly one step, with its own Architect
     and torch.optim.SGD set up as train_genomicDARTS.py:258-292 does."""
     conv, rhn = [], []
@@ -292,23 +292,26 @@ def ref_search_step(m, hyper, xt, yt, xv, yv, seed):
     opt.param_groups[1]["lr"] = hyper.rhn_lr
     opt.param_groups[1]["weight_decay"] = hyper.rhn_wd
     arch = RefArchitect(m, torch.nn.BCELoss(), _Args)
+    # P-DARTS / CWP-DARTS: the driver owns the alpha optimiser (train_genomicPDARTS.py:300-301)
+    opt_a = torch.optim.Adam(m.arch_parameters(), lr=hyper.arch_lr, betas=hyper.adam_betas,
+                             weight_decay=hyper.arch_wd) if pdarts else None
     torch.manual_seed(seed)
-    ref_tv.train([(xt, yt)], [(xv, yv)], m, rhn, conv, torch.nn.BCELoss(), opt, None, arch, False,
-                 hyper.cnn_lr, 0, 0, [5, 0.25, hyper.clip], 1000, hyper.beta, True, True, False, cfg_task)
+    ref_tv.train([(xt, yt)], [(xv, yv)], m, rhn, conv, torch.nn.BCELoss(), opt, opt_a, arch, False,
+                 hyper.cnn_lr, 0, 0, [5, 0.25, hyper.clip], 1000, hyper.beta, True, True, pdarts, cfg_task)
     return opt, arch
 
 
 cfg_task = "TF_bindings"
 
 
-def golden_model(tag, cfg, B, seed_params, full=False):
+def golden_model(tag, cfg, B, seed_params, full=False, pdarts=False):
     m = build_ref_model(cfg)
     shp = shapes_of(m)
     P = O.synthetic_params(shp, seed_params)
     xt, yt = O.synthetic_batch(B, cfg.seq_len, cfg.num_classes, 0)
     xv, yv = O.synthetic_batch(B, cfg.seq_len, cfg.num_classes, 1)
-    res = dict(cfg=cfg, B=B, seed_params=seed_params, shapes=shp)
-    hyper = O.Hyper()
+    res = dict(cfg=cfg, B=B, seed_params=seed_params, shapes=shp, pdarts=pdarts)
+    hyper = O.pdarts_hyper() if pdarts else O.Hyper()
     # ---- forward/backward with explicit masks (dropout_lin off), fp32 + fp64
     torch.manual_seed(77)
     geoms, neurons, nhid = O.cell_geometry(cfg)
@@ -369,7 +372,7 @@ def golden_model(tag, cfg, B, seed_params, full=False):
     m2 = build_ref_model(cfg, P)
     m2.dropout_lin.p = 0.0
     t0 = time.time()
-    opt, arch = ref_search_step(m2, hyper, xt, yt, xv, yv, seed=88)
+    opt, arch = ref_search_step(m2, hyper, xt, yt, xv, yv, seed=88, pdarts=pdarts)
     print(f"  ref {tag} search step {time.time() - t0:.1f}s")
     sd = m2.state_dict()
     # oracle search step with the same RNG stream for the masks (valid pass first, then train pass)
@@ -404,6 +407,61 @@ def golden_model(tag, cfg, B, seed_params, full=False):
     print("model", tag, "ok")
 
 
+def golden_genotype():
+    """Genotypes the reference derives (model_search.py:164-243) from recorded alphas."""
+    import json
+    cfg = O.SupernetConfig(seq_len=96, C=4, num_classes=10)
+    m = build_ref_model(cfg)
+    cases = []
+    for seed in range(8):
+        gen = torch.Generator().manual_seed(500 + seed)
+        scale = 1e-3 if seed < 2 else 1.0          # search starts from 1e-3 * randn alphas
+        a = [scale * torch.randn(s, generator=gen) for s in ((14, 9), (14, 9), (36, 5))]
+        with torch.no_grad():
+            m.alphas_normal.copy_(a[0]); m.alphas_reduce.copy_(a[1]); m.weights.copy_(a[2])
+        geno = m.genotype()
+        cases.append({"seed": seed, "alphas_normal": a[0].tolist(), "alphas_reduce": a[1].tolist(),
+                      "weights": a[2].tolist(),
+                      "normal": [[op, int(j)] for op, j in geno.normal], "reduce": [[op, int(j)] for op, j in geno.reduce],
+                      "rnn": [[op, int(j)] for op, j in geno.rnn], "normal_concat": list(geno.normal_concat),
+                      "reduce_concat": list(geno.reduce_concat), "rnn_concat": list(geno.rnn_concat)})
+    with open(os.path.join(GOLD, "genotype.json"), "w") as fh:
+        json.dump({"cases": cases, "how": "oracle/make_golden.py:golden_genotype -- reference RNNModelSearch.genotype()"}, fh)
+    print("genotype ok")
+
+
+def pdarts3_switches():
+    """BASELINE configs[3]: stage-3 switches of P-DARTS / CWP-DARTS, produced by the reference's OWN
+    discard_cnn_ops / discard_rhn_ops (darts_tools/discard_operations.py:25,117) run twice (9 -> 6 -> 3 CNN,
+    5 -> 3 -> 2 RNN candidates per edge) from fixed alphas, exactly as the stage loop of
+    train_genomicPDARTS.py:198-203,390-391 does.  Stored as tests/golden/pdarts3_switches.json."""
+    import copy
+    import json
+    from types import SimpleNamespace
+    from darts_tools.discard_operations import discard_cnn_ops, discard_rhn_ops
+    num_to_keep, num_to_drop = [6, 3, 1], [3, 3, 2]
+    num_to_keep_rnn, num_to_drop_rnn = [3, 2, 1], [2, 1, 1]
+    sn = [[True] * 9 for _ in range(14)]
+    sr = copy.deepcopy(sn)
+    sw = [[True] * 5 for _ in range(36)]
+    rng = np.random.RandomState(2024)
+    for sp in range(2):
+        nc, nr = sum(sn[0]), sum(sw[0])
+        model = SimpleNamespace(alphas_normal=torch.FloatTensor(rng.randn(14, nc)),
+                                alphas_reduce=torch.FloatTensor(rng.randn(14, nc)),
+                                weights=torch.FloatTensor(rng.randn(36, nr)))
+        _, _, sn, sr = discard_cnn_ops(model, sn, sr, num_to_keep, num_to_drop, sp, new_alpha_values=False)
+        _, sw = discard_rhn_ops(model, sw, num_to_keep_rnn, num_to_drop_rnn, sp, new_alpha_values=False)
+    assert all(sum(r) == 3 for r in sn + sr) and all(sum(r) == 2 for r in sw)
+    out = {"normal": [[bool(x) for x in r] for r in sn], "reduce": [[bool(x) for x in r] for r in sr],
+           "rnn": [[bool(x) for x in r] for r in sw],
+           "how": "oracle/make_golden.py:pdarts3_switches -- reference discard_cnn_ops/discard_rhn_ops, stages 0 and 1, "
+                  "alphas ~ N(0,1) from numpy RandomState(2024)"}
+    with open(os.path.join(GOLD, "pdarts3_switches.json"), "w") as fh:
+        json.dump(out, fh, indent=0)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the B=64, 4x1000, 919-label configuration")
@@ -426,6 +484,13 @@ def main():
                                switches_reduce=pruned_switches(14, 9, 3, 2),
                                switches_rnn=pruned_switches(36, 5, 2, 3))
         golden_model("tiny_pruned", cfg, 4, 42)
+    if "genotype" in todo:
+        golden_genotype()
+    if "pdarts3" in todo:
+        sw = pdarts3_switches()
+        cfg = O.SupernetConfig(dropouth=0.05, dropoutx=0.1, switches_normal=sw["normal"], switches_reduce=sw["reduce"],
+                               switches_rnn=sw["rnn"])
+        golden_model("pdarts3", cfg, 64, 44, full=True, pdarts=True)
     if args.full or "full" in todo:
         golden_model("full", O.SupernetConfig(dropouth=0.05, dropoutx=0.1), 64, 43, full=True)
 

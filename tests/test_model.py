@@ -88,15 +88,17 @@ def test_supernet_forward_backward(backend, tag, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_supernet_full_size_forward_backward(monkeypatch):
-    """BASELINE config 2: batch 64, one-hot 4x1000, 919 labels, full supernet (38.0 M parameters)."""
+@pytest.mark.parametrize("tag", ["full", "pdarts3"])
+def test_supernet_full_size_forward_backward(tag, monkeypatch):
+    """BASELINE configs[1]: batch 64, one-hot 4x1000, 919 labels, full supernet (38.0 M parameters); configs[3]: the
+    same with the P-DARTS stage-3 switches (3 CNN / 2 RNN candidates per edge)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from genome_nas_b200 import _lib
     _lib._use_library_for_tests(None, "cuda")
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    check_forward_backward(load("full"), torch.device("cuda:0"), monkeypatch)
+    check_forward_backward(load(tag), torch.device("cuda:0"), monkeypatch)
 
 
 def _args():
@@ -162,6 +164,59 @@ def test_search_step_fused_optimisers(backend, tag, monkeypatch):
     _check_step_state(m, g)
 
 
+def _hyper_of(g):
+    h = G.Hyper()
+    if g.get("pdarts"):      # P-DARTS / CWP-DARTS inline alpha step (train_and_validate.py:87-101)
+        h.arch_lr, h.adam_betas, h.arch_clip = 6e-4, (0.5, 0.999), h.clip
+    return h
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["eager", "graph"])
+@pytest.mark.parametrize("tag", ["full", "pdarts3"])
+def test_full_size_search_step(tag, mode, monkeypatch):
+    """BASELINE configs[1] (full supernet) and configs[3] (P-DARTS stage-3 switches from the reference's own
+    discard_* functions, inline clipped Adam): one B=64 search step through SearchStep, launched kernel by
+    kernel and replayed from the captured CUDA graph, against the state the reference's own train() left
+    behind (tests/golden/model_<tag>.pt: step_alphas, step_sample, step_state_norm)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from genome_nas_b200 import _lib
+    _lib._use_library_for_tests(None, "cuda")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    g = load(tag)
+    cfg = g["cfg"]
+    m, _ = build(g, dev)
+    stepper = G.SearchStep(m, hyper=_hyper_of(g))
+    mv, mt = g["step_masks"]
+    seq = [mv[0], mv[1], mt[0], mt[1]]
+    xt, yt = [t.to(dev) for t in O.synthetic_batch(g["B"], cfg.seq_len, cfg.num_classes, 0)]
+    xv, yv = [t.to(dev) for t in O.synthetic_batch(g["B"], cfg.seq_len, cfg.num_classes, 1)]
+    if mode == "eager":
+        masks = list(seq)
+        monkeypatch.setattr(R, "mask2d", lambda B, D, keep, d: masks.pop(0).to(d))
+        la, lw, raw, logits = stepper.step(xt, yt, xv, yv)
+    else:
+        # capture wants the lazily initialised state (kernel attributes, allocator pools) of one earlier eager
+        # step: run it, put the golden initial state back, then capture and replay ONCE with the golden masks
+        snap = {k: v.clone() for k, v in m.state_dict().items()}
+        stepper.step(xt, yt, xv, yv)
+        m.load_state_dict(snap)
+        for t in (stepper.mom, stepper.adam_m, stepper.adam_v, stepper.t_adam):
+            t.zero_()
+        stepper.mask_source = lambda i, B, H, keep: seq[i]
+        stepper.capture(xt, yt, xv, yv, warmup=0)
+        la, lw, raw, logits = stepper.step(xt, yt, xv, yv)
+    torch.cuda.synchronize()
+    assert abs(float(la) - float(g["step_loss_valid"])) < 1e-4 * abs(float(g["step_loss_valid"]))
+    assert abs(float(lw) - float(g["step_loss_train"])) < 1e-4 * abs(float(g["step_loss_train"]))
+    # full size: the reference's own fp32 step and its fp64-exact restatement differ by up to 8e-4 on the
+    # near-zero running means (make_golden.py: step_oracle_vs_ref_worst) -> 4x the tiny-model tolerances
+    _check_step_state(m, g, tol_scale=4.0)
+
+
 def test_seeded_construction_matches_reference_initialisation():
     """Same constructor calls in the same order as the reference => identical initial weights for a seed.
     Known answer from SURVEY.md 8(c): sum |params| = 800971.928 for seed 3 on the full supernet."""
@@ -177,6 +232,26 @@ def test_seeded_construction_matches_reference_initialisation():
     total = sum(float(p.detach().double().abs().sum()) for p in m.parameters())
     assert abs(total - 800971.928) < 0.05
     assert torch.allclose(m.alphas_normal[0, :3].detach(), torch.tensor([1.78863e-3, 4.36510e-4, 9.64975e-5]), rtol=1e-4)
+
+
+def test_genotype_matches_reference():
+    """genotype() against the reference's own derivation (model_search.py:164-243) on recorded alphas
+    (tests/golden/genotype.json, written by oracle/make_golden.py:golden_genotype)."""
+    import json
+    gold = json.load(open(os.path.join(GOLDEN, "genotype.json")))
+    g = load("tiny")
+    m, _ = build(g, torch.device("cpu"))
+    assert len(gold["cases"]) >= 6
+    for case in gold["cases"]:
+        with torch.no_grad():
+            m.alphas_normal.copy_(torch.tensor(case["alphas_normal"]))
+            m.alphas_reduce.copy_(torch.tensor(case["alphas_reduce"]))
+            m.weights.copy_(torch.tensor(case["weights"]))
+        geno = m.genotype()
+        for field in ("normal", "reduce", "rnn"):
+            assert [[op, int(j)] for op, j in getattr(geno, field)] == case[field], (case["seed"], field)
+        for field in ("normal_concat", "reduce_concat", "rnn_concat"):
+            assert list(getattr(geno, field)) == case[field], (case["seed"], field)
 
 
 def test_genotype_and_api_surface():
