@@ -363,6 +363,8 @@ def golden_model(tag, cfg, B, seed_params, full=False, pdarts=False):
     # every tensor: <g, r_i> with r_i ~ N(0,1) from generator seed 1000+i (direction check without storing g)
     res["grad_dot64"] = {n: float((g.double().flatten() * probe_vec(i, g.numel())).sum())
                          for i, (n, g) in enumerate(grads["64"].items())}
+    if full:   # every tensor: a sketch that estimates the actual rel-L2 error (O.sketch)
+        res["grad_sketch64"] = {n: O.sketch(g, i) for i, (n, g) in enumerate(grads["64"].items())}
     # a projection of the big decoder gradient
     gen = torch.Generator().manual_seed(3)
     v = torch.randn(grads["64"]["decoder.weight"].shape[1], generator=gen, dtype=torch.float64)

@@ -70,6 +70,11 @@ def check_forward_backward(g, device, monkeypatch):
         lim = max(1e-3, 1.5 * r32[n])
         if n in g["grad64"]:
             score[n] = relerr(p.grad, g["grad64"][n]) / lim
+        elif "grad_sketch64" in g:
+            # full-size goldens: S random projections of the fp64 gradient per tensor; sqrt(mean_k <g - g_ref, r_k>^2)
+            # is an unbiased estimate of ||g - g_ref|| (O.sketch: sigma 6 % at S = 128)
+            d = O.sketch(p.grad, i) - g["grad_sketch64"][n]
+            score[n] = float(d.pow(2).mean().sqrt()) / (lim * ref)
         else:
             gd = p.grad.detach().double().cpu()
             dot = float((gd.flatten() * probe_vec(i, gd.numel())).sum())
