@@ -4,8 +4,9 @@ TEST / BASELINE INFRASTRUCTURE ONLY (never imported by the product package).
 
 The reference (GenomeNet/Genome-NAS) is pure Python: there is nothing to link.  Its "compiled form" is CPython
 bytecode, so this recipe runs `py_compile` on the reference modules of the hot path directly from
-/root/reference (read-only; no source is copied into the repository) and writes sourceless `.pyc` modules
-into oracle/_ref/ (git-ignored, NOT gpurun-ignored: it travels to the GPU box like the built libgnas.so).
+/root/reference (read-only; no source is copied into the repository) and writes sourceless bytecode modules
+(`*.gnasref`: the gpurun snapshot drops `*.pyc`) into oracle/_ref/ (git-ignored, NOT gpurun-ignored: it travels
+to the GPU box like the built libgnas.so).  `load()` installs a meta-path finder that imports them.
 `bench.py --impl reference` and the `cpu_baseline` / `gpu_eager_baseline` legs import the reference from
 there and run ITS OWN train() / Architect / model classes; when oracle/_ref/ is absent they fall back to the
 restatement in oracle/genomenas_oracle.py (`kind: "port"`).
@@ -44,8 +45,11 @@ MODULES = [
 ]
 
 
+EXT = ".gnasref"
+
+
 def available():
-    return os.path.isfile(os.path.join(OUT, "model_search.pyc"))
+    return os.path.isfile(os.path.join(OUT, "model_search" + EXT))
 
 
 def build(force=False):
@@ -58,13 +62,30 @@ def build(force=False):
         return True
     for rel in MODULES:
         src = os.path.join(REFERENCE, rel)
-        dst = os.path.join(OUT, rel[:-3] + ".pyc")
+        dst = os.path.join(OUT, rel[:-3] + EXT)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         py_compile.compile(src, cfile=dst, dfile=rel, doraise=True,
                            invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     with open(stamp, "w") as fh:
         fh.write(want)
     return True
+
+
+class _RefFinder:
+    """meta-path finder: module `a.b` <- oracle/_ref/a/b.gnasref (or a/b/__init__.gnasref), sourceless bytecode"""
+
+    @staticmethod
+    def find_spec(name, path=None, target=None):
+        from importlib.machinery import SourcelessFileLoader
+        from importlib.util import spec_from_file_location
+        base = os.path.join(OUT, *name.split("."))
+        if os.path.isfile(base + EXT):
+            return spec_from_file_location(name, base + EXT, loader=SourcelessFileLoader(name, base + EXT))
+        init = os.path.join(base, "__init__" + EXT)
+        if os.path.isfile(init):
+            return spec_from_file_location(name, init, loader=SourcelessFileLoader(name, init),
+                                           submodule_search_locations=[base])
+        return None
 
 
 def load():
@@ -76,8 +97,8 @@ def load():
     import types
     for m in ("matplotlib", "matplotlib.pyplot"):
         sys.modules.setdefault(m, types.ModuleType(m))
-    if OUT not in sys.path:
-        sys.path.insert(0, OUT)
+    if not any(f is _RefFinder for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefFinder)
     import model_search
     from darts_tools import architect, discard_operations, model_discCNN
     from generalNAS_tools import train_and_validate
