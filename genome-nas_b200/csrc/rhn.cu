@@ -70,9 +70,25 @@ struct RhnTable {             // per edge p = i(i+1)/2 + j: index into probs for
   short pidx[GNAS_RNN_EDGES][4];
 };
 
+}  // namespace gnas
+#include "rhn_tc.cuh"
+namespace gnas {
+
+// The tensor-core forward (rhn_tc.cuh) is the default wherever its shape constraints hold; GNAS_RHN_TC=0 (or
+// GNAS_TC=0 on the GPU) selects the fp32 CUDA-core kernel below, which also serves the other shapes.
+static inline bool rhn_tc_wanted() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GNAS_RHN_TC"); v = e ? atoi(e) : 1; }
+#ifndef GNAS_EMUL
+  return v != 0 && tc_enabled();
+#else
+  return v != 0;
+#endif
+}
+
 struct RhnPlan {
   int BP;
-  long long xmT, xkT, hmT, h0T, ring, ST, CHT, C0T, HT, stat, bar, fwd_total;   // forward workspace (floats)
+  long long xmT, xkT, hmT, h0T, ring, ST, CHT, C0T, HT, stat, bar, tc, fwd_total;   // forward workspace (floats)
   long long dsT, dhT, dxT, doT, dpacc, WsT, W0T, bwd_zero, bwd_total;           // backward scratch
 };
 
@@ -93,6 +109,8 @@ static RhnPlan rhn_plan(const GnasRhnDesc* d) {
   p.HT = o; o += T * HB;           // h_t^T
   p.stat = o; o += T * 9 * 2 * H;
   p.bar = o; o += 256;             // barrier counter + abort flag (+ debug timing marks)
+  p.tc = o;                        // operands of the tensor-core forward: x, state ring, packed weights (hi | lo)
+  if (H % rtc::KCH == 0 && d->B <= rtc::BPT) o += rtc::plan(d->T, d->H).total;
   p.fwd_total = o;
   o = 0;
   p.dpacc = o; o += 2 * 36 * 4;    // doubles
@@ -861,6 +879,49 @@ extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const floa
   f.out = out; f.running = bn_running;
   f.bar = reinterpret_cast<unsigned*>(ws + p.bar); f.abort_flag = reinterpret_cast<int*>(ws + p.bar) + 8;
   rhn_table(d, f.tb);
+  {
+    int nsm = 1 << 30;
+#ifndef GNAS_EMUL
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+#endif
+    if (rhn_tc_wanted() && rtc::supported(d->B, H, nsm)) {
+      const rtc::Plan tp = rtc::plan(d->T, H);
+      float* tcw = ws + p.tc;
+      rtc::Pre pre;
+      pre.T = d->T; pre.H = H; pre.BP = BP; pre.xmT = ws + p.xmT; pre.h0T = ws + p.h0T; pre.hmT = ws + p.hmT;
+      pre.xc = tcw + tp.xc; pre.ring9 = tcw + tp.ringc + 9LL * tp.nch * rtc::S_CHUNK;
+      GNAS_LAUNCH(rtc::k_rhn_tc_pre, dim3(ewb((long long)(d->T + 1) * H * rtc::BPT)), dim3(256), 0, st, pre);
+      rtc::Pack pk;
+      pk.H = H; pk.W0 = W0; pk.Ws = Ws; pk.wp = tcw + tp.wp; pk.wp_cta = tp.wp_cta;
+      GNAS_LAUNCH(rtc::k_rhn_tc_pack, dim3(H / rtc::NC), dim3(256), 0, st, pk);
+      rtc::Fwd f;
+      f.T = d->T; f.B = d->B; f.BP = BP; f.H = H; f.training = d->training; f.momentum = d->bn_momentum;
+      f.hmT = ws + p.hmT; f.h0T = ws + p.h0T; f.probs = probs;
+      f.xc = tcw + tp.xc; f.ringc = tcw + tp.ringc; f.wp = tcw + tp.wp; f.wp_cta = tp.wp_cta;
+      f.ST = ws + p.ST; f.CHT = ws + p.CHT; f.C0T = ws + p.C0T; f.HT = ws + p.HT; f.stat = ws + p.stat;
+      f.out = out; f.running = bn_running; f.bar = reinterpret_cast<unsigned*>(ws + p.bar);
+      rhn_table(d, f.tb);
+      const size_t tsm = rtc::smem_bytes();
+      const int tgrid = H / rtc::NC;
+#ifdef GNAS_EMUL
+      GNAS_LAUNCH_COOP(rtc::k_rhn_fwd_tc, dim3(tgrid), dim3(rtc::THREADS), tsm, st, f);
+#else
+      static int prepared[kMaxDevices] = {0};
+      if (need_prepare(prepared, (int)tsm)) {
+        cudaError_t e = cudaFuncSetAttribute(rtc::k_rhn_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        if (e != cudaSuccess) { set_error("rhn_forward: shared memory request rejected (tensor-core kernel)"); return (int)e; }
+      }
+      void* targs[] = {(void*)&f};
+      prof_before("k_rhn_fwd_tc", "", st);
+      cudaError_t e = cudaLaunchCooperativeKernel((void*)rtc::k_rhn_fwd_tc, dim3(tgrid), dim3(rtc::THREADS), targs, tsm, st);
+      prof_after(st);
+      if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
+#endif
+      return check_launch("gnas_rhn_forward");
+    }
+  }
   const size_t smem = sizeof(float) * ((size_t)2 * H * 8 + (size_t)8 * H * 8 + (size_t)kStages * kKCH * BP +
                                        8 * BP * 4 + 9 * BP * 4 + 3 * BP * 4 + 36 * 5 + 8 + 8);
   const int grid = H / kNC;

@@ -1,0 +1,470 @@
+// Recurrent highway layer, forward, on the 5th-generation tensor cores (error-compensated 3xTF32).
+// Replaces the recurrent products of darts_tools/model_discCNN.py:255-268 ([x_t*xm | h*hm] W0) and
+// model_search.py:68-79 ((s_j*hm) Ws[i] for every edge (i, j)) -- the per-step batch x nhid GEMMs north_star (2)
+// asks to put on tensor-core MMA -- inside ONE persistent cooperative kernel.
+//
+// Decomposition.  CTA g owns NC = 4 hidden columns n0 = 4g .. 4g+3, i.e. the 8 output columns (c | h) of W0 and
+// of each Ws[i].  A time step is 9 dependent stages: stage 0 produces s_0 from [x_t | h_{t-1}], stage s = j + 1
+// multiplies the new state s_j with the slices of Ws[j..7] ("multiply on arrival": the edge (j, j) completes
+// node j -> s_{j+1}, the other 7 - j products are parked in the accumulators of their nodes).  Per stage:
+//     D[64 batch rows][R columns] = S[64][K = H] * Wslice[K][R],   R = 8 (8 - j)  (8 for stage 0, K = 2H)
+// as tcgen05.mma.kind::tf32 with M = 64 (batch), N = R, K = 8 per instruction; both operands are pre-split into
+// tf32 hi + lo and three products (hi*hi, hi*lo, lo*hi) accumulate in fp32 in tensor memory -- hi*hi alternates
+// between two accumulators, the cross terms use a third (the tensor core truncates on accumulate, so short chains
+// matter: profiles/README.md item 8).  Measured on a B200 (tools/umma_probe.cu): an M = 64 instruction costs
+// 27 cycles for N <= 32 and 33 for N = 64 (the shared-memory read of A), so the batch is the M side.
+//
+// Data movement.  Nothing but the operands of the next MMAs is ever staged: the masked state is PUBLISHED by its
+// producer already split into hi | lo and laid out as the K-major no-swizzle UMMA operand ([4-column group][batch]
+// [4]), so a consumer fetches a 64-column K chunk (32 KB) with one TMA bulk copy into a 3-slot ring; the weight
+// slices are packed once per call (k_rhn_tc_pack) into the same layout and streamed by a cp.async warp (only the
+// R rows a stage needs).  BatchNorm over the batch is per column, hence CTA-local; a grid barrier separates stages.
+//
+// Warp roles (352 threads): warps 0-7 epilogue (TMEM -> shared, gates, BatchNorm, publish, stash for backward),
+// warp 8 state producer (grid-barrier wait + TMA), warp 9 MMA issuer (one elected lane), warp 10 weight loader.
+// The same source is compiled for the CPU emulator against a functional model of mbarrier / bulk copy / tcgen05
+// (tests/emul/tc_emul.h), which is how the layouts and hand-offs are tested without a GPU.
+#pragma once
+#include "tc_common.cuh"
+
+namespace gnas {
+namespace rtc {
+
+using namespace gnas::tc;
+
+constexpr int NC = 4;                    // hidden columns per CTA
+constexpr int BPT = 64;                  // batch rows of the MMA (padded)
+constexpr int KCH = 64;                  // K per pipeline chunk
+constexpr int KC4 = KCH / 4;             // 4-column groups (core-matrix columns) per chunk
+constexpr int NSLOT = 3;
+constexpr int S_HALF = KC4 * BPT * 4;    // floats of the hi (or lo) half of a state chunk (16 KB)
+constexpr int S_CHUNK = 2 * S_HALF;      // 32 KB
+constexpr int R0 = 2 * NC;               // output columns of one weight matrix per CTA (c | h)
+constexpr int RMAX = 8 * R0;             // stage 1: all eight Ws
+constexpr int W_CHUNK_MAX = 2 * KC4 * RMAX * 4;
+constexpr int SLOT = S_CHUNK + W_CHUNK_MAX;          // floats per ring slot (64 KB)
+constexpr int PITCH = 72;                // part[column][batch] pitch: conflict-free for the dump and for (batch, column) readers
+constexpr int EPI = 256;                 // epilogue threads: (batch row m = tid / 4, column = tid % 4)
+constexpr int THREADS = EPI + 96;
+constexpr int TM_COLS = 256;             // 3 accumulators x 64 columns
+
+struct Plan {
+  int nch;                               // K chunks per H
+  long long xc, ringc, wp, total;        // extra forward workspace (floats): x operands, state ring, packed weights
+  long long wp_cta;                      // packed floats per CTA
+};
+static inline Plan plan(int T, int H) {
+  Plan p;
+  p.nch = H / KCH;
+  long long o = 0;
+  p.xc = o; o += (long long)T * p.nch * S_CHUNK;
+  p.ringc = o; o += 10LL * p.nch * S_CHUNK;
+  p.wp_cta = (long long)p.nch * (2 * 2 * KC4 * R0 * 4 + 2 * KC4 * RMAX * 4);
+  p.wp = o; o += (long long)(H / NC) * p.wp_cta;
+  p.total = o;
+  return p;
+}
+static inline bool supported(int B, int H, int nsm) { return B >= 1 && B <= BPT && H % KCH == 0 && H / NC <= nsm; }
+
+// offset (floats) of element (hidden column n, batch row m) inside a [nch][hi|lo][KC4][BPT][4] operand buffer
+__device__ __forceinline__ long long op_off(int n, int m, int lo) {
+  const int g4 = n >> 2;
+  return (long long)(g4 / KC4) * S_CHUNK + (long long)lo * S_HALF + ((g4 % KC4) * BPT + m) * 4 + (n & 3);
+}
+
+// ------------------------------------------------------------------ per-call preparation
+// x operands of every time step and the initial hidden state, masked, split and laid out (from the feature-major
+// buffers the prologue of rhn.cu wrote)
+struct Pre { int T, H, BP; const float* xmT; const float* h0T; const float* hmT; float* xc; float* ring9; };
+static __global__ void __launch_bounds__(256) k_rhn_tc_pre(const __grid_constant__ Pre P) {
+  const long long HB = (long long)P.H * BPT;
+  const long long total = (long long)(P.T + 1) * HB;
+  const long long slab_f = (long long)(P.H / KCH) * S_CHUNK;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / HB);
+    const int r = (int)(i - (long long)t * HB);
+    const int m = r % BPT, n = r / BPT;
+    float v = 0.f;
+    if (m < P.BP) v = t < P.T ? P.xmT[((long long)t * P.H + n) * P.BP + m] : P.h0T[(long long)n * P.BP + m] * P.hmT[(long long)n * P.BP + m];
+    const float hi = __uint_as_float(to_tf32(v));
+    float* dst = t < P.T ? P.xc + (long long)t * slab_f : P.ring9;
+    dst[op_off(n, m, 0)] = hi;
+    dst[op_off(n, m, 1)] = __uint_as_float(to_tf32(v - hi));
+  }
+}
+
+// weights -> per-CTA operand slices, hi | lo:  [W0 x part: nch x [2][KC4][R0][4]] [W0 h part: same]
+// [Ws: nch x [2][KC4][RMAX][4]], Ws rows = (block b = 7 - i, c|h, column): stage j reads the first 8 (8 - j) rows.
+struct Pack { int H; const float* W0; const float* Ws; float* wp; long long wp_cta; };
+static __global__ void __launch_bounds__(256) k_rhn_tc_pack(const __grid_constant__ Pack P) {
+  const int H = P.H, nch = H / KCH;
+  const int g = blockIdx.x, n0 = g * NC;
+  float* out = P.wp + (long long)g * P.wp_cta;
+  const int per0 = nch * KC4 * R0 * 4;             // elements of one W0 half (x or h rows), one of hi/lo
+  const int perS = nch * KC4 * RMAX * 4;
+  for (int e = threadIdx.x; e < 2 * per0 + perS; e += blockDim.x) {
+    float v;
+    long long dst_hi;
+    if (e < 2 * per0) {
+      const int part = e / per0, q = e - part * per0;
+      const int c4 = q & 3, r = (q >> 2) % R0, g4 = (q >> 2) / R0;      // g4: 4-column group of K over the whole H
+      const int k = part * H + g4 * 4 + c4;
+      v = P.W0[(long long)k * 2 * H + (r / NC) * H + n0 + (r % NC)];
+      dst_hi = (long long)part * (2 * per0) + (long long)(g4 / KC4) * (2 * KC4 * R0 * 4) + ((g4 % KC4) * R0 + r) * 4 + c4;
+      out[dst_hi] = __uint_as_float(to_tf32(v));
+      out[dst_hi + KC4 * R0 * 4] = __uint_as_float(to_tf32(v - __uint_as_float(to_tf32(v))));
+    } else {
+      const int q = e - 2 * per0;
+      const int c4 = q & 3, r = (q >> 2) % RMAX, g4 = (q >> 2) / RMAX;
+      const int i = 7 - r / R0, rr = r % R0;
+      const int k = g4 * 4 + c4;
+      v = P.Ws[((long long)i * H + k) * 2 * H + (rr / NC) * H + n0 + (rr % NC)];
+      dst_hi = 4LL * per0 + (long long)(g4 / KC4) * (2 * KC4 * RMAX * 4) + ((g4 % KC4) * RMAX + r) * 4 + c4;
+      out[dst_hi] = __uint_as_float(to_tf32(v));
+      out[dst_hi + KC4 * RMAX * 4] = __uint_as_float(to_tf32(v - __uint_as_float(to_tf32(v))));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ the persistent forward kernel
+struct Fwd {
+  int T, B, BP, H, training;
+  float momentum;
+  const float* hmT; const float* h0T; const float* probs;
+  const float* xc; float* ringc; const float* wp; long long wp_cta;
+  float* ST; float* CHT; float* C0T; float* HT; float* stat;
+  float* out; float* running;
+  unsigned* bar;
+  RhnTable tb;
+};
+
+struct Job { int t, stage, chunk, first, last; };     // chunk: index inside the stage
+// jobs of a time step: stage 0 = 2 nch chunks (x then h), stages 1..8 = nch chunks each
+__device__ __forceinline__ Job job_of(long long q, int nch) {
+  const int per_t = 10 * nch;
+  Job j;
+  j.t = (int)(q / per_t);
+  const int r = (int)(q - (long long)j.t * per_t);
+  if (r < 2 * nch) { j.stage = 0; j.chunk = r; j.first = r == 0; j.last = r == 2 * nch - 1; }
+  else { j.stage = 1 + (r - 2 * nch) / nch; j.chunk = (r - 2 * nch) % nch; j.first = j.chunk == 0; j.last = j.chunk == nch - 1; }
+  return j;
+}
+__device__ __forceinline__ int rows_of(int stage) { return stage == 0 ? R0 : R0 * (9 - stage); }
+
+__device__ __forceinline__ void spin_until(const unsigned* bar, unsigned target) {
+  const long long t0 = gnas_clock();
+  while (ld_acquire_u32(bar) < target) {
+    GNAS_SPIN_PAUSE();
+#ifndef GNAS_EMUL
+    if (gnas_clock() - t0 > 4000000000LL) __trap();      // ~2 s: never leave the GPU spinning
+#endif
+  }
+  (void)t0;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant__ Fwd P) {
+  const int H = P.H, B = P.B, T = P.T, nch = H / KCH;
+  const int n0 = blockIdx.x * NC;
+  const int tid = threadIdx.x, lane = tid & 31;
+#ifdef GNAS_EMUL
+  const int warp = tid >> 5;
+#else
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+#endif
+  const long long HB = (long long)H * P.BP;            // stash tensors keep the caller's padded batch pitch
+  GNAS_DYN_SMEM(float, smem);
+  float* ring = smem;                                    // NSLOT x { S chunk | W chunk }
+  float* part = ring + (size_t)NSLOT * SLOT;             // [RMAX][PITCH] D of the stage, column-major
+  float* pp = part + RMAX * PITCH;                       // [36][4] probabilities
+  float* pq = pp + 36 * 4;                               // [36]
+  float* red = pq + 36;                                  // [2][8 warps][NC] BatchNorm partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * 8 * NC + 4);   // 8-byte aligned: all counts above are even
+  uint64_t* bar_full = bars;                             // [NSLOT] state bytes + weight loader
+  uint64_t* bar_empty = bars + NSLOT;                    // [NSLOT] MMAs of the slot retired
+  uint64_t* bar_acc_full = bars + 2 * NSLOT;             // accumulators of a stage complete
+  uint64_t* bar_acc_empty = bars + 2 * NSLOT + 1;        // ... and copied out of tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 2);
+  const long long njobs = (long long)T * 10 * nch;
+
+  if (tid < 36) {
+    float q = 0.f;
+    for (int k = 0; k < 4; ++k) {
+      const int ix = P.tb.pidx[tid][k];
+      const float v = ix >= 0 ? P.probs[ix] : 0.f;
+      pp[tid * 4 + k] = v; q += v;
+    }
+    pq[tid] = q;
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TM_COLS);
+  if (tid == 32) {
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }
+    mbar_init(bar_acc_full, 1); mbar_init(bar_acc_empty, 1);
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+  const float* wp = P.wp + (long long)blockIdx.x * P.wp_cta;
+  const int per0 = nch * 2 * KC4 * R0 * 4;               // floats of one W0 half (hi + lo)
+
+  if (warp == 8) {
+    // ================= state producer: one lane; TMA bulk copy of a 32 KB operand chunk per job
+    if (lane == 0) {
+      for (long long q = 0; q < njobs; ++q) {
+        const int s = (int)(q % NSLOT);
+        const Job j = job_of(q, nch);
+        if (q >= NSLOT) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
+        const float* src;
+        if (j.stage == 0 && j.chunk < nch) src = P.xc + ((long long)j.t * nch + j.chunk) * S_CHUNK;
+        else {
+          // barrier number = publishes completed: s_{stage-1} of this step is publish t*9 + stage; h_{t-1} is t*9
+          const int slot = j.stage == 0 ? 9 : j.stage - 1;
+          const int c = j.stage == 0 ? j.chunk - nch : j.chunk;
+          const long long nb = (long long)j.t * 9 + j.stage;
+          if (nb > 0 && c == 0) { spin_until(P.bar, (unsigned)(nb * gridDim.x)); fence_proxy_async_all(); }
+          src = P.ringc + ((long long)slot * nch + c) * S_CHUNK;
+        }
+        mbar_expect_tx(&bar_full[s], S_CHUNK * 4);
+        bulk_g2s(ring + (size_t)s * SLOT, src, S_CHUNK * 4, &bar_full[s]);
+      }
+    }
+  } else if (warp == 10) {
+    // ================= weight loader: cp.async of the R rows the stage needs, one group per job, two in flight
+    for (long long q = 0; q <= njobs; ++q) {
+      if (q < njobs) {
+        const int s = (int)(q % NSLOT);
+        const Job j = job_of(q, nch);
+        if (q >= NSLOT) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
+        const int R = rows_of(j.stage);
+        const float* src;
+        int RS;
+        if (j.stage == 0) { src = wp + (long long)(j.chunk / nch) * per0 + (long long)(j.chunk % nch) * (2 * KC4 * R0 * 4); RS = R0; }
+        else { src = wp + 2LL * per0 + (long long)j.chunk * (2 * KC4 * RMAX * 4); RS = RMAX; }
+        float* dst = ring + (size_t)s * SLOT + S_CHUNK;
+        for (int idx = lane; idx < 2 * KC4 * R; idx += 32) {
+          const int g = idx / R, r = idx - g * R;
+          cp_async16(dst + (size_t)idx * 4, src + ((size_t)g * RS + r) * 4);
+        }
+      }
+      cp_async_commit();
+      if (q >= 1) {            // the group of job q - 1 has landed: hand it to the MMA warp
+        cp_async_wait<1>();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[(q - 1) % NSLOT]);
+      }
+    }
+  } else if (warp == 9) {
+    // ================= MMA issuer
+    long long sg = 0;                                   // stage counter over the whole sequence
+    int u = 0;                                          // K step inside the stage
+    for (long long q = 0; q < njobs; ++q) {
+      const int s = (int)(q % NSLOT);
+      const Job j = job_of(q, nch);
+      const int R = rows_of(j.stage);
+      if (j.first) {
+        u = 0;
+        if (sg > 0) mbar_wait(bar_acc_empty, (uint32_t)((sg - 1) & 1));
+      }
+      mbar_wait(&bar_full[s], (uint32_t)((q / NSLOT) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_mn(64, R);
+        const uint32_t sbase = smem_u32(ring + (size_t)s * SLOT);
+        const uint32_t wbase = sbase + S_CHUNK * 4;
+        const uint32_t lbo_a = BPT * 16, lbo_b = (uint32_t)R * 16;
+#pragma unroll
+        for (int ks = 0; ks < KCH / 8; ++ks) {
+          const uint64_t ah = make_desc(sbase + ks * 2 * lbo_a, lbo_a, 128);
+          const uint64_t al = make_desc(sbase + S_HALF * 4 + ks * 2 * lbo_a, lbo_a, 128);
+          const uint64_t bh = make_desc(wbase + ks * 2 * lbo_b, lbo_b, 128);
+          const uint64_t bl = make_desc(wbase + KC4 * (uint32_t)R * 16 + ks * 2 * lbo_b, lbo_b, 128);
+          const int uu = u + ks;
+          mma_tf32(tmem_d + (uu & 1) * 64, ah, bh, idesc, (uint32_t)(uu >= 2));    // hi*hi: two accumulators in turn
+          mma_tf32(tmem_d + 128, ah, bl, idesc, (uint32_t)(uu > 0));                 // cross terms: third accumulator
+          mma_tf32(tmem_d + 128, al, bh, idesc, 1);
+        }
+        mma_commit(&bar_empty[s]);
+        if (j.last) mma_commit(bar_acc_full);
+      }
+      u += KCH / 8;
+      if (j.last) ++sg;
+      __syncwarp();
+    }
+  } else if (warp < 8) {
+    // ================= epilogue: thread = (batch row m, own column col)
+    const int m = tid >> 2, col = tid & 3, n = n0 + col;
+    const bool real = m < B;
+    const int q4 = warp & 3, hf = warp >> 2;            // TMEM lane quarter / column half of this warp
+    const float hmask = real ? P.hmT[(long long)n * P.BP + m] : 0.f;
+    float hprev = real ? P.h0T[(long long)n * P.BP + m] : 0.f;
+    float run_mean = 0.f, run_var = 1.f;
+    if (P.running) { run_mean = P.running[n]; run_var = P.running[H + n]; }
+    float accn[8], sl[9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) accn[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sl[i] = 0.f;
+    const float invB = 1.f / (float)B;
+    int flip = 0;
+    // sum over the batch of `v` for this thread's column (fixed order: deterministic); all 256 threads take part
+    auto batch_sum = [&](float v) -> float {
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      float* r = red + flip * 8 * NC;
+      flip ^= 1;
+      if (lane < NC) r[warp * NC + lane] = v;
+      named_bar_sync(1, EPI);
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += r[w * NC + col];
+      return t;
+    };
+    // BatchNorm over the batch of the raw state -> s (own copy), stats stash, publish masked hi | lo into ring slot
+    auto bn_publish = [&](float raw, int t, int stage, int slot) -> float {
+      float mean, rstd;
+      if (P.training) {
+        mean = batch_sum(real ? raw : 0.f) * invB;
+        const float d = real ? raw - mean : 0.f;
+        const float var = batch_sum(d * d) * invB;
+        rstd = 1.0f / sqrtf(var + kBnEps);
+        run_mean = (1.f - P.momentum) * run_mean + P.momentum * mean;
+        run_var = (1.f - P.momentum) * run_var + P.momentum * (B > 1 ? var * (float)B / (float)(B - 1) : var);
+      } else {
+        mean = run_mean;
+        rstd = 1.0f / sqrtf(run_var + kBnEps);
+      }
+      const float v = real ? (raw - mean) * rstd : 0.f;
+      if (m == 0) { float* st = P.stat + ((long long)t * 9 + stage) * 2 * H; st[n] = mean; st[H + n] = rstd; }
+      if (m < P.BP) P.ST[((long long)t * 9 + stage) * HB + (long long)n * P.BP + m] = v;
+      if (slot >= 0) {
+        const float mv = v * hmask;
+        const float hi = __uint_as_float(to_tf32(mv));
+        float* dst = P.ringc + (long long)slot * nch * S_CHUNK;
+        dst[op_off(n, m, 0)] = hi;
+        dst[op_off(n, m, 1)] = __uint_as_float(to_tf32(mv - hi));
+      }
+      return v;
+    };
+    auto publish_done = [&]() {
+      fence_proxy_async_all();
+      named_bar_sync(2, EPI);
+      if (tid == 0) { __threadfence(); atomicAdd(P.bar, 1u); }
+    };
+    // contribution of edge (i, j) with pre-activations c | h to node i
+    auto edge = [&](int i, int j, float c, float h) -> float {
+      const int p = i * (i + 1) / 2 + j;
+      const float q = pq[p];
+      const float p0 = pp[p * 4], p1 = pp[p * 4 + 1], p2 = pp[p * 4 + 2], p3 = pp[p * 4 + 3];
+      if (p0 == 0.f && p1 == 0.f && p2 == 0.f && p3 == 0.f) return 0.f;
+      const float sj = sl[j];
+      const float g = sigmoidf_(c);
+      float F = 0.f;
+      if (p0 != 0.f) F = fmaf(p0, tanhf(h), F);
+      if (p1 != 0.f) F = fmaf(p1, h, F);
+      if (p2 != 0.f) F = fmaf(p2, sigmoidf_(h), F);
+      if (p3 != 0.f) F = fmaf(p3, h > 0.f ? h : 0.f, F);
+      return q * sj + g * (F - q * sj);
+    };
+
+    long long sg = 0;
+    for (int t = 0; t < T; ++t) {
+      for (int stage = 0; stage < 9; ++stage, ++sg) {
+        const int R = rows_of(stage);
+        // ---- accumulators -> shared memory (column-major, three partial accumulators summed)
+        mbar_wait(bar_acc_full, (uint32_t)(sg & 1));
+        tc_fence_after();
+        if (32 * hf < R) {
+          float v[32], w[32];
+          const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(32 * hf);
+          tmem_ld32(taddr, v);
+          tmem_ld32(taddr + 64, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
+          tmem_ld32(taddr + 128, w);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += w[i];
+          if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (32 * hf + i < R) part[(32 * hf + i) * PITCH + 16 * q4 + lane] = v[i];
+          }
+        }
+        tc_fence_before();
+        named_bar_sync(3, EPI);
+        if (tid == 0) { tc_fence_after(); mbar_arrive(bar_acc_empty); }
+        if (stage == 0) {
+          // ---- s_0 = BN(h + sig(c0) (tanh(h0) - h))     (model_discCNN.py:258-268)
+          const float c = part[col * PITCH + m], h = part[(NC + col) * PITCH + m];
+          if (m < P.BP) {
+            P.C0T[((long long)t * 2 + 0) * HB + (long long)n * P.BP + m] = real ? c : 0.f;
+            P.C0T[((long long)t * 2 + 1) * HB + (long long)n * P.BP + m] = real ? h : 0.f;
+          }
+          const float raw = hprev + sigmoidf_(c) * (tanhf(h) - hprev);
+          sl[0] = bn_publish(raw, t, 0, 0);
+          publish_done();
+        } else {
+          const int j = stage - 1;
+          // ---- critical: edge (j, j) completes node j -> s_{j+1}   (model_search.py:68-93)
+          const int rb = (7 - j) * R0;                      // its rows are the last block of the operand
+          const float cc = part[(rb + col) * PITCH + m], hh = part[(rb + NC + col) * PITCH + m];
+          float raw = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i == j) { accn[i] += edge(i, j, cc, hh); raw = accn[i]; accn[i] = 0.f; }
+          const float v = bn_publish(raw, t, stage, stage < 8 ? stage : -1);
+#pragma unroll
+          for (int i = 1; i < 9; ++i) if (i == stage) sl[i] = v;
+          if (stage == 8) {
+            // h_t = mean(s_1..s_8)   (model_search.py:96); its masked copy feeds stage 0 of the next step
+            float a = 0.f;
+#pragma unroll
+            for (int i = 1; i <= 8; ++i) a += sl[i];
+            a = real ? a * 0.125f : 0.f;
+            hprev = a;
+            const float mv = a * hmask;
+            const float hi = __uint_as_float(to_tf32(mv));
+            float* dst = P.ringc + 9LL * nch * S_CHUNK;
+            dst[op_off(n, m, 0)] = hi;
+            dst[op_off(n, m, 1)] = __uint_as_float(to_tf32(mv - hi));
+            if (m < P.BP) P.HT[(long long)t * HB + (long long)n * P.BP + m] = a;
+            if (real) P.out[((long long)t * B + m) * H + n] = a;
+          }
+          publish_done();
+          // ---- off the critical path: stash the pre-activations, park the other products of s_j in their nodes
+          if (m < P.BP) {
+            float* chp = P.CHT + (((long long)t * 36 + j * (j + 1) / 2 + j) * 2) * HB + (long long)n * P.BP + m;
+            chp[0] = real ? cc : 0.f; chp[HB] = real ? hh : 0.f;
+          }
+#pragma unroll
+          for (int b = 0; b < 7; ++b) {
+            const int i = 7 - b;
+            if (i > j) {
+              const float c = part[(b * R0 + col) * PITCH + m], h = part[(b * R0 + NC + col) * PITCH + m];
+              if (m < P.BP) {
+                float* chp = P.CHT + (((long long)t * 36 + i * (i + 1) / 2 + j) * 2) * HB + (long long)n * P.BP + m;
+                chp[0] = real ? c : 0.f; chp[HB] = real ? h : 0.f;
+              }
+              accn[i] += edge(i, j, c, h);
+            }
+          }
+        }
+        // `part` is rewritten by the next stage's dump: everyone must be done reading it
+        named_bar_sync(4, EPI);
+      }
+    }
+    if (P.training && P.running && m == 0) { P.running[n] = run_mean; P.running[H + n] = run_var; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_d, TM_COLS); }
+}
+
+static inline size_t smem_bytes() {
+  return sizeof(float) * ((size_t)NSLOT * SLOT + RMAX * PITCH + 36 * 4 + 36 + 2 * 8 * NC + 4) + 8 * (2 * NSLOT + 2) + 16;
+}
+
+}  // namespace rtc
+}  // namespace gnas

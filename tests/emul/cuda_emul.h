@@ -76,6 +76,7 @@ struct Warp {
   unsigned gen = 0;
   int nlanes = 32;
 };
+struct NamedBarrier { int arrived = 0; unsigned gen = 0; };
 struct Block {
   uint3_ bid;
   dim3 bdim, gdim;
@@ -85,6 +86,8 @@ struct Block {
   std::vector<Fiber> fibers;
   std::vector<Warp> warps;
   unsigned char* dyn_smem = nullptr;
+  NamedBarrier named[16];                 // bar.sync id, count
+  std::vector<float> tmem;                // tensor memory of the CTA: [128 lanes][512 columns], allocated on demand
 };
 
 extern thread_local Fiber* cur;
@@ -177,3 +180,4 @@ using std::max;
 using std::min;
 
 #define GNAS_EMUL_YIELD() emul::yield()
+#include "tc_emul.h"
