@@ -9,19 +9,25 @@
 // node j -> s_{j+1}, the other 7 - j products are parked in the accumulators of their nodes).  Per stage:
 //     D[64 batch rows][R columns] = S[64][K = H] * Wslice[K][R],   R = 8 (8 - j)  (8 for stage 0, K = 2H)
 // as tcgen05.mma.kind::tf32 with M = 64 (batch), N = R, K = 8 per instruction; both operands are pre-split into
-// tf32 hi + lo and three products (hi*hi, hi*lo, lo*hi) accumulate in fp32 in tensor memory -- hi*hi alternates
-// between two accumulators, the cross terms use a third (the tensor core truncates on accumulate, so short chains
-// matter: profiles/README.md item 8).  Measured on a B200 (tools/umma_probe.cu): an M = 64 instruction costs
-// 27 cycles for N <= 32 and 33 for N = 64 (the shared-memory read of A), so the batch is the M side.
+// tf32 hi + lo and three products (hi*hi, hi*lo, lo*hi) accumulate in fp32 in tensor memory.  The tensor core
+// TRUNCATES when it adds into the accumulator; in a 378-stage recurrence that bias does not average out (one
+// 64-step chain per stage: output error 2.1e-5 at T = 42 against 5.9e-6 for fp32 FFMA, measured and reproduced
+// by a truncation model).  So the chains are kept to ONE 64-column K chunk (hi*hi alternating between two
+// accumulators, the cross terms in a third), the epilogue warps drain every chunk into fp32 registers
+// (round-to-nearest adds) while the next chunk multiplies into the second accumulator set: 2.5e-6 in the model.
+// Measured on a B200 (tools/umma_probe.cu): an M = 64 instruction costs 27 cycles for N <= 32 and 33 for N = 64
+// (the shared-memory read of A), so the batch is the M side.
 //
 // Data movement.  Nothing but the operands of the next MMAs is ever staged: the masked state is PUBLISHED by its
 // producer already split into hi | lo and laid out as the K-major no-swizzle UMMA operand ([4-column group][batch]
 // [4]), so a consumer fetches a 64-column K chunk (32 KB) with one TMA bulk copy into a 3-slot ring; the weight
-// slices are packed once per call (k_rhn_tc_pack) into the same layout and streamed by a cp.async warp (only the
-// R rows a stage needs).  BatchNorm over the batch is per column, hence CTA-local; a grid barrier separates stages.
+// slices are packed once per call (k_rhn_tc_pack) block-major ([chunk][matrix i = 7..0][hi|lo][4-column group][8
+// rows][4]: SBO = one block, LBO = 128 bytes), so the 8 (8 - j) rows stage j needs are ONE contiguous bulk copy.
+// BatchNorm over the batch is per column, hence CTA-local; a grid barrier separates stages.
 //
-// Warp roles (352 threads): warps 0-7 epilogue (TMEM -> shared, gates, BatchNorm, publish, stash for backward),
-// warp 8 state producer (grid-barrier wait + TMA), warp 9 MMA issuer (one elected lane), warp 10 weight loader.
+// Warp roles (352 threads): warps 0-7 epilogue (TMEM -> registers -> shared, gates, BatchNorm, publish, stash for
+// backward), warp 8 state producer (grid-barrier wait + TMA), warp 9 MMA issuer (one elected lane), warp 10
+// weight producer (TMA).
 // The same source is compiled for the CPU emulator against a functional model of mbarrier / bulk copy / tcgen05
 // (tests/emul/tc_emul.h), which is how the layouts and hand-offs are tested without a GPU.
 #pragma once
@@ -41,12 +47,13 @@ constexpr int S_HALF = KC4 * BPT * 4;    // floats of the hi (or lo) half of a s
 constexpr int S_CHUNK = 2 * S_HALF;      // 32 KB
 constexpr int R0 = 2 * NC;               // output columns of one weight matrix per CTA (c | h)
 constexpr int RMAX = 8 * R0;             // stage 1: all eight Ws
-constexpr int W_CHUNK_MAX = 2 * KC4 * RMAX * 4;
+constexpr int W_BLOCK = 2 * KC4 * R0 * 4;  // floats of one matrix block of a chunk: [hi|lo][KC4][R0][4] (4 KB)
+constexpr int W_CHUNK_MAX = 8 * W_BLOCK;
 constexpr int SLOT = S_CHUNK + W_CHUNK_MAX;          // floats per ring slot (64 KB)
 constexpr int PITCH = 72;                // part[column][batch] pitch: conflict-free for the dump and for (batch, column) readers
 constexpr int EPI = 256;                 // epilogue threads: (batch row m = tid / 4, column = tid % 4)
 constexpr int THREADS = EPI + 96;
-constexpr int TM_COLS = 256;             // 3 accumulators x 64 columns
+constexpr int TM_COLS = 512;             // 2 sets x (3 accumulators x 64 columns, set pitch 256)
 
 struct Plan {
   int nch;                               // K chunks per H
@@ -59,7 +66,7 @@ static inline Plan plan(int T, int H) {
   long long o = 0;
   p.xc = o; o += (long long)T * p.nch * S_CHUNK;
   p.ringc = o; o += 10LL * p.nch * S_CHUNK;
-  p.wp_cta = (long long)p.nch * (2 * 2 * KC4 * R0 * 4 + 2 * KC4 * RMAX * 4);
+  p.wp_cta = (long long)p.nch * (2 * W_BLOCK + 8 * W_BLOCK);
   p.wp = o; o += (long long)(H / NC) * p.wp_cta;
   p.total = o;
   return p;
@@ -93,36 +100,33 @@ static __global__ void __launch_bounds__(256) k_rhn_tc_pre(const __grid_constant
   }
 }
 
-// weights -> per-CTA operand slices, hi | lo:  [W0 x part: nch x [2][KC4][R0][4]] [W0 h part: same]
-// [Ws: nch x [2][KC4][RMAX][4]], Ws rows = (block b = 7 - i, c|h, column): stage j reads the first 8 (8 - j) rows.
+// weights -> per-CTA operand slices, block-major: [W0 x part: nch x block] [W0 h part: nch x block]
+// [Ws: nch x 8 blocks, block b = matrix i = 7 - b], block = [hi|lo][KC4][R0 rows = (c|h, column)][4].
+// Stage j reads the first 8 - j blocks of a chunk.
 struct Pack { int H; const float* W0; const float* Ws; float* wp; long long wp_cta; };
 static __global__ void __launch_bounds__(256) k_rhn_tc_pack(const __grid_constant__ Pack P) {
   const int H = P.H, nch = H / KCH;
   const int g = blockIdx.x, n0 = g * NC;
   float* out = P.wp + (long long)g * P.wp_cta;
-  const int per0 = nch * KC4 * R0 * 4;             // elements of one W0 half (x or h rows), one of hi/lo
-  const int perS = nch * KC4 * RMAX * 4;
-  for (int e = threadIdx.x; e < 2 * per0 + perS; e += blockDim.x) {
+  const int half = KC4 * R0 * 4;                    // one of hi / lo of a block
+  const int nblk = 2 * nch + 8 * nch;               // blocks of this CTA in packing order
+  for (int e = threadIdx.x; e < nblk * half; e += blockDim.x) {
+    const int blk = e / half, q = e - blk * half;
+    const int c4 = q & 3, rr = (q >> 2) % R0, kcc = (q >> 2) / R0;
+    const int col = (rr / NC) * H + n0 + (rr % NC);
     float v;
-    long long dst_hi;
-    if (e < 2 * per0) {
-      const int part = e / per0, q = e - part * per0;
-      const int c4 = q & 3, r = (q >> 2) % R0, g4 = (q >> 2) / R0;      // g4: 4-column group of K over the whole H
-      const int k = part * H + g4 * 4 + c4;
-      v = P.W0[(long long)k * 2 * H + (r / NC) * H + n0 + (r % NC)];
-      dst_hi = (long long)part * (2 * per0) + (long long)(g4 / KC4) * (2 * KC4 * R0 * 4) + ((g4 % KC4) * R0 + r) * 4 + c4;
-      out[dst_hi] = __uint_as_float(to_tf32(v));
-      out[dst_hi + KC4 * R0 * 4] = __uint_as_float(to_tf32(v - __uint_as_float(to_tf32(v))));
+    if (blk < 2 * nch) {
+      const int k = blk * KCH + kcc * 4 + c4;         // blk = part * nch + chunk: rows 0..2H-1 of W0 in order
+      v = P.W0[(long long)k * 2 * H + col];
     } else {
-      const int q = e - 2 * per0;
-      const int c4 = q & 3, r = (q >> 2) % RMAX, g4 = (q >> 2) / RMAX;
-      const int i = 7 - r / R0, rr = r % R0;
-      const int k = g4 * 4 + c4;
-      v = P.Ws[((long long)i * H + k) * 2 * H + (rr / NC) * H + n0 + (rr % NC)];
-      dst_hi = 4LL * per0 + (long long)(g4 / KC4) * (2 * KC4 * RMAX * 4) + ((g4 % KC4) * RMAX + r) * 4 + c4;
-      out[dst_hi] = __uint_as_float(to_tf32(v));
-      out[dst_hi + KC4 * RMAX * 4] = __uint_as_float(to_tf32(v - __uint_as_float(to_tf32(v))));
+      const int chunk = (blk - 2 * nch) / 8, i = 7 - (blk - 2 * nch) % 8;
+      const int k = chunk * KCH + kcc * 4 + c4;
+      v = P.Ws[((long long)i * H + k) * 2 * H + col];
     }
+    const float hi = __uint_as_float(to_tf32(v));
+    float* dst = out + (long long)blk * W_BLOCK + q;
+    dst[0] = hi;
+    dst[half] = __uint_as_float(to_tf32(v - hi));
   }
 }
 
@@ -162,7 +166,19 @@ __device__ __forceinline__ void spin_until(const unsigned* bar, unsigned target)
   (void)t0;
 }
 
+#ifdef GNAS_RHN_TIMING
+// clock64 marks of CTA 0 at time step 1 (tools/rhn_timing.py): [stage][0 first chunk complete, 1 drained + dumped,
+// 2 published (barrier arrive), 3 stage end, 4 producer passed the grid barrier, 5 MMA warp saw the first chunk,
+// 6 MMA warp issued the last chunk]
+#define RTC_MARK(stage, k) do { if (blockIdx.x == 0 && t_mark == 1) dbg[(stage) * 8 + (k)] = clock64(); } while (0)
+#else
+#define RTC_MARK(stage, k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant__ Fwd P) {
+#ifdef GNAS_RHN_TIMING
+  long long* dbg = reinterpret_cast<long long*>(P.bar + 16);
+#endif
   const int H = P.H, B = P.B, T = P.T, nch = H / KCH;
   const int n0 = blockIdx.x * NC;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -179,11 +195,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
   float* pq = pp + 36 * 4;                               // [36]
   float* red = pq + 36;                                  // [2][8 warps][NC] BatchNorm partials
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * 8 * NC + 4);   // 8-byte aligned: all counts above are even
-  uint64_t* bar_full = bars;                             // [NSLOT] state bytes + weight loader
+  uint64_t* bar_full = bars;                             // [NSLOT] state bytes + weight bytes of a chunk
   uint64_t* bar_empty = bars + NSLOT;                    // [NSLOT] MMAs of the slot retired
-  uint64_t* bar_acc_full = bars + 2 * NSLOT;             // accumulators of a stage complete
-  uint64_t* bar_acc_empty = bars + 2 * NSLOT + 1;        // ... and copied out of tensor memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 2);
+  uint64_t* bar_acc_full = bars + 2 * NSLOT;             // [2] accumulator set of a chunk complete
+  uint64_t* bar_acc_empty = bars + 2 * NSLOT + 2;        // [2] ... and drained into registers by all 8 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 4);
   const long long njobs = (long long)T * 10 * nch;
 
   if (tid < 36) {
@@ -198,7 +214,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
   if (warp == 0) tmem_alloc(tmem_slot, TM_COLS);
   if (tid == 32) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }
-    mbar_init(bar_acc_full, 1); mbar_init(bar_acc_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }
     mbar_fence_init();
   }
   tc_fence_before();
@@ -206,7 +222,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
   const float* wp = P.wp + (long long)blockIdx.x * P.wp_cta;
-  const int per0 = nch * 2 * KC4 * R0 * 4;               // floats of one W0 half (hi + lo)
 
   if (warp == 8) {
     // ================= state producer: one lane; TMA bulk copy of a 32 KB operand chunk per job
@@ -222,7 +237,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
           const int slot = j.stage == 0 ? 9 : j.stage - 1;
           const int c = j.stage == 0 ? j.chunk - nch : j.chunk;
           const long long nb = (long long)j.t * 9 + j.stage;
-          if (nb > 0 && c == 0) { spin_until(P.bar, (unsigned)(nb * gridDim.x)); fence_proxy_async_all(); }
+          if (nb > 0 && c == 0) {
+            spin_until(P.bar, (unsigned)(nb * gridDim.x));
+            fence_proxy_async_all();
+#ifdef GNAS_RHN_TIMING
+            { const int t_mark = j.t; RTC_MARK(j.stage, 4); }
+#endif
+          }
           src = P.ringc + ((long long)slot * nch + c) * S_CHUNK;
         }
         mbar_expect_tx(&bar_full[s], S_CHUNK * 4);
@@ -230,66 +251,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
       }
     }
   } else if (warp == 10) {
-    // ================= weight loader: cp.async of the R rows the stage needs, one group per job, two in flight
-    for (long long q = 0; q <= njobs; ++q) {
-      if (q < njobs) {
+    // ================= weight producer: one lane; the 8 - j leading blocks of the chunk in ONE bulk copy
+    if (lane == 0) {
+      for (long long q = 0; q < njobs; ++q) {
         const int s = (int)(q % NSLOT);
         const Job j = job_of(q, nch);
         if (q >= NSLOT) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
-        const int R = rows_of(j.stage);
-        const float* src;
-        int RS;
-        if (j.stage == 0) { src = wp + (long long)(j.chunk / nch) * per0 + (long long)(j.chunk % nch) * (2 * KC4 * R0 * 4); RS = R0; }
-        else { src = wp + 2LL * per0 + (long long)j.chunk * (2 * KC4 * RMAX * 4); RS = RMAX; }
-        float* dst = ring + (size_t)s * SLOT + S_CHUNK;
-        for (int idx = lane; idx < 2 * KC4 * R; idx += 32) {
-          const int g = idx / R, r = idx - g * R;
-          cp_async16(dst + (size_t)idx * 4, src + ((size_t)g * RS + r) * 4);
-        }
-      }
-      cp_async_commit();
-      if (q >= 1) {            // the group of job q - 1 has landed: hand it to the MMA warp
-        cp_async_wait<1>();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_full[(q - 1) % NSLOT]);
+        const float* src = j.stage == 0 ? wp + (long long)j.chunk * W_BLOCK
+                                        : wp + 2LL * nch * W_BLOCK + (long long)j.chunk * 8 * W_BLOCK;
+        const uint32_t bytes = (uint32_t)(j.stage == 0 ? 1 : 9 - j.stage) * W_BLOCK * 4;
+        mbar_expect_tx(&bar_full[s], bytes);
+        bulk_g2s(ring + (size_t)s * SLOT + S_CHUNK, src, bytes, &bar_full[s]);
       }
     }
   } else if (warp == 9) {
-    // ================= MMA issuer
-    long long sg = 0;                                   // stage counter over the whole sequence
-    int u = 0;                                          // K step inside the stage
+    // ================= MMA issuer: every chunk starts fresh accumulators in set q & 1
     for (long long q = 0; q < njobs; ++q) {
-      const int s = (int)(q % NSLOT);
+      const int s = (int)(q % NSLOT), set = (int)(q & 1);
       const Job j = job_of(q, nch);
       const int R = rows_of(j.stage);
-      if (j.first) {
-        u = 0;
-        if (sg > 0) mbar_wait(bar_acc_empty, (uint32_t)((sg - 1) & 1));
-      }
+      if (q >= 2) mbar_wait(&bar_acc_empty[set], (uint32_t)((q / 2 - 1) & 1));
       mbar_wait(&bar_full[s], (uint32_t)((q / NSLOT) & 1));
       tc_fence_after();
       if (elect_one()) {
+#ifdef GNAS_RHN_TIMING
+        { const int t_mark = j.t; if (j.first || (j.stage == 0 && j.chunk == nch)) RTC_MARK(j.stage, 5); }
+#endif
         const uint32_t idesc = make_idesc_mn(64, R);
         const uint32_t sbase = smem_u32(ring + (size_t)s * SLOT);
         const uint32_t wbase = sbase + S_CHUNK * 4;
-        const uint32_t lbo_a = BPT * 16, lbo_b = (uint32_t)R * 16;
+        const uint32_t acc = tmem_d + (uint32_t)set * 256;
+        constexpr uint32_t lbo_a = BPT * 16, lbo_b = R0 * 16, sbo_b = W_BLOCK * 4, w_lo = KC4 * R0 * 16;
 #pragma unroll
         for (int ks = 0; ks < KCH / 8; ++ks) {
           const uint64_t ah = make_desc(sbase + ks * 2 * lbo_a, lbo_a, 128);
           const uint64_t al = make_desc(sbase + S_HALF * 4 + ks * 2 * lbo_a, lbo_a, 128);
-          const uint64_t bh = make_desc(wbase + ks * 2 * lbo_b, lbo_b, 128);
-          const uint64_t bl = make_desc(wbase + KC4 * (uint32_t)R * 16 + ks * 2 * lbo_b, lbo_b, 128);
-          const int uu = u + ks;
-          mma_tf32(tmem_d + (uu & 1) * 64, ah, bh, idesc, (uint32_t)(uu >= 2));    // hi*hi: two accumulators in turn
-          mma_tf32(tmem_d + 128, ah, bl, idesc, (uint32_t)(uu > 0));                 // cross terms: third accumulator
-          mma_tf32(tmem_d + 128, al, bh, idesc, 1);
+          const uint64_t bh = make_desc(wbase + ks * 2 * lbo_b, lbo_b, sbo_b);
+          const uint64_t bl = make_desc(wbase + w_lo + ks * 2 * lbo_b, lbo_b, sbo_b);
+          mma_tf32(acc + (ks & 1) * 64, ah, bh, idesc, (uint32_t)(ks >= 2));     // hi*hi: two accumulators in turn
+          mma_tf32(acc + 128, ah, bl, idesc, (uint32_t)(ks > 0));                  // cross terms: third accumulator
+          mma_tf32(acc + 128, al, bh, idesc, 1);
         }
         mma_commit(&bar_empty[s]);
-        if (j.last) mma_commit(bar_acc_full);
+        mma_commit(&bar_acc_full[set]);
+#ifdef GNAS_RHN_TIMING
+        { const int t_mark = j.t; if (j.last) RTC_MARK(j.stage, 6); }
+#endif
       }
-      u += KCH / 8;
-      if (j.last) ++sg;
       __syncwarp();
     }
   } else if (warp < 8) {
@@ -353,6 +361,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
       named_bar_sync(2, EPI);
       if (tid == 0) { __threadfence(); atomicAdd(P.bar, 1u); }
     };
+#ifdef GNAS_RHN_TIMING
+#define RTC_PUBLISHED(stage) do { const int t_mark = t; if (tid == 0) RTC_MARK(stage, 2); } while (0)
+#else
+#define RTC_PUBLISHED(stage) do { } while (0)
+#endif
     // contribution of edge (i, j) with pre-activations c | h to node i
     auto edge = [&](int i, int j, float c, float h) -> float {
       const int p = i * (i + 1) / 2 + j;
@@ -369,32 +382,46 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
       return q * sj + g * (F - q * sj);
     };
 
-    long long sg = 0;
+    long long qe = 0;                                   // chunk (job) counter, same order as the MMA warp
     for (int t = 0; t < T; ++t) {
-      for (int stage = 0; stage < 9; ++stage, ++sg) {
+      for (int stage = 0; stage < 9; ++stage) {
         const int R = rows_of(stage);
-        // ---- accumulators -> shared memory (column-major, three partial accumulators summed)
-        mbar_wait(bar_acc_full, (uint32_t)(sg & 1));
-        tc_fence_after();
-        if (32 * hf < R) {
-          float v[32], w[32];
-          const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(32 * hf);
-          tmem_ld32(taddr, v);
-          tmem_ld32(taddr + 64, w);
+        // ---- drain every chunk's accumulators into fp32 registers (round-to-nearest), then -> shared memory
+        const int njs = stage == 0 ? 2 * nch : nch;
+        float racc[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += w[i];
-          tmem_ld32(taddr + 128, w);
+        for (int i = 0; i < 32; ++i) racc[i] = 0.f;
+        for (int c = 0; c < njs; ++c, ++qe) {
+          const int set = (int)(qe & 1);
+          mbar_wait(&bar_acc_full[set], (uint32_t)((qe / 2) & 1));
+          tc_fence_after();
+#ifdef GNAS_RHN_TIMING
+          { const int t_mark = t; if (tid == 0 && c == (stage == 0 ? nch : 0)) RTC_MARK(stage, 0); }
+#endif
+          if (32 * hf < R) {
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(set * 256 + 32 * hf);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += w[i];
-          if (lane < 16) {
+            for (int a = 0; a < 3; ++a) {
+              float v[32];
+              tmem_ld32(taddr + a * 64, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (32 * hf + i < R) part[(32 * hf + i) * PITCH + 16 * q4 + lane] = v[i];
+              for (int i = 0; i < 32; ++i) racc[i] += v[i];
+            }
           }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[set]);
         }
-        tc_fence_before();
+        if (32 * hf < R && lane < 16) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * hf + i < R) part[(32 * hf + i) * PITCH + 16 * q4 + lane] = racc[i];
+        }
         named_bar_sync(3, EPI);
-        if (tid == 0) { tc_fence_after(); mbar_arrive(bar_acc_empty); }
+#ifdef GNAS_RHN_TIMING
+        const int t_mark = t;
+        if (tid == 0) RTC_MARK(stage, 1);
+#endif
         if (stage == 0) {
           // ---- s_0 = BN(h + sig(c0) (tanh(h0) - h))     (model_discCNN.py:258-268)
           const float c = part[col * PITCH + m], h = part[(NC + col) * PITCH + m];
@@ -405,6 +432,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
           const float raw = hprev + sigmoidf_(c) * (tanhf(h) - hprev);
           sl[0] = bn_publish(raw, t, 0, 0);
           publish_done();
+          RTC_PUBLISHED(0);
         } else {
           const int j = stage - 1;
           // ---- critical: edge (j, j) completes node j -> s_{j+1}   (model_search.py:68-93)
@@ -433,6 +461,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
             if (real) P.out[((long long)t * B + m) * H + n] = a;
           }
           publish_done();
+          RTC_PUBLISHED(stage);
           // ---- off the critical path: stash the pre-activations, park the other products of s_j in their nodes
           if (m < P.BP) {
             float* chp = P.CHT + (((long long)t * 36 + j * (j + 1) / 2 + j) * 2) * HB + (long long)n * P.BP + m;
@@ -453,6 +482,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
         }
         // `part` is rewritten by the next stage's dump: everyone must be done reading it
         named_bar_sync(4, EPI);
+#ifdef GNAS_RHN_TIMING
+        if (tid == 0) RTC_MARK(stage, 3);
+#endif
       }
     }
     if (P.training && P.running && m == 0) { P.running[n] = run_mean; P.running[H + n] = run_var; }
@@ -463,7 +495,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
 }
 
 static inline size_t smem_bytes() {
-  return sizeof(float) * ((size_t)NSLOT * SLOT + RMAX * PITCH + 36 * 4 + 36 + 2 * 8 * NC + 4) + 8 * (2 * NSLOT + 2) + 16;
+  return sizeof(float) * ((size_t)NSLOT * SLOT + RMAX * PITCH + 36 * 4 + 36 + 2 * 8 * NC + 4) + 8 * (2 * NSLOT + 4) + 16;
 }
 
 }  // namespace rtc
