@@ -22,12 +22,13 @@
 // producer already split into hi | lo and laid out as the K-major no-swizzle UMMA operand ([4-column group][batch]
 // [4]), so a consumer fetches a 64-column K chunk (32 KB) with one TMA bulk copy into a 3-slot ring; the weight
 // slices are packed once per call (k_rhn_tc_pack) block-major ([chunk][matrix i = 7..0][hi|lo][4-column group][8
-// rows][4]: SBO = one block, LBO = 128 bytes), so the 8 (8 - j) rows stage j needs are ONE contiguous bulk copy.
+// rows][4]: SBO = one block, LBO = 128 bytes), so the 8 (8 - j) rows stage j needs are one contiguous range.
 // BatchNorm over the batch is per column, hence CTA-local; a grid barrier separates stages.
 //
-// Warp roles (352 threads): warps 0-7 epilogue (TMEM -> registers -> shared, gates, BatchNorm, publish, stash for
-// backward), warp 8 state producer (grid-barrier wait + TMA), warp 9 MMA issuer (one elected lane), warp 10
-// weight producer (TMA).
+// Warp roles (384 threads): warps 0-7 epilogue (TMEM -> registers -> shared, gates, BatchNorm, publish, stash for
+// backward), warp 8 state producer (grid-barrier wait + TMA), warp 9 MMA issuer (one elected lane), warps 10-11
+// weight loaders (cp.async: a 1-D bulk copy costs ~600 cycles of the TMA unit whatever its size -- measured, two
+// per chunk made the unit the bottleneck -- so only the state goes through it).
 // The same source is compiled for the CPU emulator against a functional model of mbarrier / bulk copy / tcgen05
 // (tests/emul/tc_emul.h), which is how the layouts and hand-offs are tested without a GPU.
 #pragma once
@@ -52,7 +53,7 @@ constexpr int W_CHUNK_MAX = 8 * W_BLOCK;
 constexpr int SLOT = S_CHUNK + W_CHUNK_MAX;          // floats per ring slot (64 KB)
 constexpr int PITCH = 72;                // part[column][batch] pitch: conflict-free for the dump and for (batch, column) readers
 constexpr int EPI = 256;                 // epilogue threads: (batch row m = tid / 4, column = tid % 4)
-constexpr int THREADS = EPI + 96;
+constexpr int THREADS = EPI + 128;           // + state producer, MMA issuer, two weight-loader warps
 constexpr int TM_COLS = 512;             // 2 sets x (3 accumulators x 64 columns, set pitch 256)
 
 struct Plan {
@@ -158,8 +159,9 @@ __device__ __forceinline__ int rows_of(int stage) { return stage == 0 ? R0 : R0 
 __device__ __forceinline__ void spin_until(const unsigned* bar, unsigned target) {
   const long long t0 = gnas_clock();
   while (ld_acquire_u32(bar) < target) {
+#ifdef GNAS_EMUL
     GNAS_SPIN_PAUSE();
-#ifndef GNAS_EMUL
+#else
     if (gnas_clock() - t0 > 4000000000LL) __trap();      // ~2 s: never leave the GPU spinning
 #endif
   }
@@ -169,7 +171,7 @@ __device__ __forceinline__ void spin_until(const unsigned* bar, unsigned target)
 #ifdef GNAS_RHN_TIMING
 // clock64 marks of CTA 0 at time step 1 (tools/rhn_timing.py): [stage][0 first chunk complete, 1 drained + dumped,
 // 2 published (barrier arrive), 3 stage end, 4 producer passed the grid barrier, 5 MMA warp saw the first chunk,
-// 6 MMA warp issued the last chunk]
+// 6 MMA warp issued the last chunk, 7 BatchNorm + stores issued]
 #define RTC_MARK(stage, k) do { if (blockIdx.x == 0 && t_mark == 1) dbg[(stage) * 8 + (k)] = clock64(); } while (0)
 #else
 #define RTC_MARK(stage, k) do { } while (0)
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
   }
   if (warp == 0) tmem_alloc(tmem_slot, TM_COLS);
   if (tid == 32) {
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 3); mbar_init(&bar_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }
     mbar_fence_init();
   }
@@ -250,18 +252,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
         bulk_g2s(ring + (size_t)s * SLOT, src, S_CHUNK * 4, &bar_full[s]);
       }
     }
-  } else if (warp == 10) {
-    // ================= weight producer: one lane; the 8 - j leading blocks of the chunk in ONE bulk copy
-    if (lane == 0) {
-      for (long long q = 0; q < njobs; ++q) {
+  } else if (warp >= 10) {
+    // ================= weight loaders (2 warps): the 8 - j leading blocks of the chunk are one contiguous range;
+    // cp.async 16 bytes per lane, one group per job, the previous job's group is handed over while this one flies
+    const int lw = warp - 10;
+    for (long long q = 0; q <= njobs; ++q) {
+      if (q < njobs) {
         const int s = (int)(q % NSLOT);
         const Job j = job_of(q, nch);
         if (q >= NSLOT) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
         const float* src = j.stage == 0 ? wp + (long long)j.chunk * W_BLOCK
                                         : wp + 2LL * nch * W_BLOCK + (long long)j.chunk * 8 * W_BLOCK;
-        const uint32_t bytes = (uint32_t)(j.stage == 0 ? 1 : 9 - j.stage) * W_BLOCK * 4;
-        mbar_expect_tx(&bar_full[s], bytes);
-        bulk_g2s(ring + (size_t)s * SLOT + S_CHUNK, src, bytes, &bar_full[s]);
+        const int pieces = (j.stage == 0 ? 1 : 9 - j.stage) * (W_BLOCK / 4);      // 16-byte pieces
+        float* dst = ring + (size_t)s * SLOT + S_CHUNK;
+        for (int idx = lw * 32 + lane; idx < pieces; idx += 64) cp_async16(dst + (size_t)idx * 4, src + (size_t)idx * 4);
+      }
+      cp_async_commit();
+      if (q >= 1) {
+        cp_async_wait<1>();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[(q - 1) % NSLOT]);
       }
     }
   } else if (warp == 9) {
@@ -357,7 +368,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
       return v;
     };
     auto publish_done = [&]() {
-      fence_proxy_async_all();
       named_bar_sync(2, EPI);
       if (tid == 0) { __threadfence(); atomicAdd(P.bar, 1u); }
     };
@@ -431,6 +441,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
           }
           const float raw = hprev + sigmoidf_(c) * (tanhf(h) - hprev);
           sl[0] = bn_publish(raw, t, 0, 0);
+#ifdef GNAS_RHN_TIMING
+          if (tid == 0) RTC_MARK(0, 7);
+#endif
           publish_done();
           RTC_PUBLISHED(0);
         } else {
@@ -443,6 +456,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
           for (int i = 0; i < 8; ++i)
             if (i == j) { accn[i] += edge(i, j, cc, hh); raw = accn[i]; accn[i] = 0.f; }
           const float v = bn_publish(raw, t, stage, stage < 8 ? stage : -1);
+#ifdef GNAS_RHN_TIMING
+          if (tid == 0) RTC_MARK(stage, 7);
+#endif
 #pragma unroll
           for (int i = 1; i < 9; ++i) if (i == stage) sl[i] = v;
           if (stage == 8) {

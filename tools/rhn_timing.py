@@ -52,7 +52,8 @@ if os.environ.get("GNAS_RHN_TC", "1") != "0":
         v = [int(marks[s, k]) - base for k in range(8)]
         line = f"{s}: {v[4]:9d} {v[5]:9d} {v[0]:9d} {v[1]:9d} {v[2]:9d} {v[3]:9d} {v[6]:9d}"
         if prev_pub is not None:
-            line += f"   publish->barrier {v[4] - prev_pub:6d}  barrier->dumped {v[1] - v[4]:6d}  dumped->published {v[2] - v[1]:6d}"
+            line += (f"   publish->barrier {v[4] - prev_pub:6d}  barrier->dumped {v[1] - v[4]:6d}  dumped->bn+stores {v[7] - v[1]:6d}"
+                     f"  ->published {v[2] - v[7]:6d}")
         prev_pub = v[2]
         print(line)
     print("time step cycles (published stage 8 - barrier stage 0):", int(marks[8, 2]) - base)
