@@ -12,9 +12,9 @@
 // tf32 hi + lo and three products (hi*hi, hi*lo, lo*hi) accumulate in fp32 in tensor memory.  The tensor core
 // TRUNCATES when it adds into the accumulator; in a 378-stage recurrence that bias does not average out (one
 // 64-step chain per stage: output error 2.1e-5 at T = 42 against 5.9e-6 for fp32 FFMA, measured and reproduced
-// by a truncation model).  So the chains are kept to ONE 64-column K chunk (hi*hi alternating between two
-// accumulators, the cross terms in a third), the epilogue warps drain every chunk into fp32 registers
-// (round-to-nearest adds) while the next chunk multiplies into the second accumulator set: 2.5e-6 in the model.
+// by a truncation model).  So the chains are kept to ONE 64-column K chunk (8 hi*hi products in one accumulator,
+// the 16 cross terms in a second), and the epilogue warps drain every chunk into fp32 registers (round-to-nearest
+// adds) while the next chunks multiply into the other three accumulator sets: fp32-class error in the model.
 // Measured on a B200 (tools/umma_probe.cu): an M = 64 instruction costs 27 cycles for N <= 32 and 33 for N = 64
 // (the shared-memory read of A), so the batch is the M side.
 //
@@ -54,7 +54,8 @@ constexpr int SLOT = S_CHUNK + W_CHUNK_MAX;          // floats per ring slot (64
 constexpr int PITCH = 72;                // part[column][batch] pitch: conflict-free for the dump and for (batch, column) readers
 constexpr int EPI = 256;                 // epilogue threads: (batch row m = tid / 4, column = tid % 4)
 constexpr int THREADS = EPI + 128;           // + state producer, MMA issuer, two weight-loader warps
-constexpr int TM_COLS = 512;             // 2 sets x (3 accumulators x 64 columns, set pitch 256)
+constexpr int NSET = 4;                  // accumulator sets in tensor memory: {hi*hi, cross terms} x 64 columns each
+constexpr int TM_COLS = NSET * 128;
 
 struct Plan {
   int nch;                               // K chunks per H
@@ -199,9 +200,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * 8 * NC + 4);   // 8-byte aligned: all counts above are even
   uint64_t* bar_full = bars;                             // [NSLOT] state bytes + weight bytes of a chunk
   uint64_t* bar_empty = bars + NSLOT;                    // [NSLOT] MMAs of the slot retired
-  uint64_t* bar_acc_full = bars + 2 * NSLOT;             // [2] accumulator set of a chunk complete
-  uint64_t* bar_acc_empty = bars + 2 * NSLOT + 2;        // [2] ... and drained into registers by all 8 epilogue warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 4);
+  uint64_t* bar_acc_full = bars + 2 * NSLOT;             // [NSET] accumulator set of a chunk complete
+  uint64_t* bar_acc_empty = bars + 2 * NSLOT + NSET;     // [NSET] ... and drained into registers by all 8 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSLOT + 2 * NSET);
   const long long njobs = (long long)T * 10 * nch;
 
   if (tid < 36) {
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
   if (warp == 0) tmem_alloc(tmem_slot, TM_COLS);
   if (tid == 32) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 3); mbar_init(&bar_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }
+    for (int i = 0; i < NSET; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }
     mbar_fence_init();
   }
   tc_fence_before();
@@ -260,7 +261,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
       if (q < njobs) {
         const int s = (int)(q % NSLOT);
         const Job j = job_of(q, nch);
-        if (q >= NSLOT) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
+        if (q >= NSLOT && lane == 0) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
+        __syncwarp();
         const float* src = j.stage == 0 ? wp + (long long)j.chunk * W_BLOCK
                                         : wp + 2LL * nch * W_BLOCK + (long long)j.chunk * 8 * W_BLOCK;
         const int pieces = (j.stage == 0 ? 1 : 9 - j.stage) * (W_BLOCK / 4);      // 16-byte pieces
@@ -276,13 +278,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
       }
     }
   } else if (warp == 9) {
-    // ================= MMA issuer: every chunk starts fresh accumulators in set q & 1
+    // ================= MMA issuer: every chunk starts fresh accumulators in set q % NSET
     for (long long q = 0; q < njobs; ++q) {
-      const int s = (int)(q % NSLOT), set = (int)(q & 1);
+      const int s = (int)(q % NSLOT), set = (int)(q % NSET);
       const Job j = job_of(q, nch);
       const int R = rows_of(j.stage);
-      if (q >= 2) mbar_wait(&bar_acc_empty[set], (uint32_t)((q / 2 - 1) & 1));
-      mbar_wait(&bar_full[s], (uint32_t)((q / NSLOT) & 1));
+      if (lane == 0) {            // one lane polls (32 pollers on one mbarrier only slow the arrivals down)
+        if (q >= NSET) mbar_wait(&bar_acc_empty[set], (uint32_t)((q / NSET - 1) & 1));
+        mbar_wait(&bar_full[s], (uint32_t)((q / NSLOT) & 1));
+      }
+      __syncwarp();
       tc_fence_after();
       if (elect_one()) {
 #ifdef GNAS_RHN_TIMING
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
         const uint32_t idesc = make_idesc_mn(64, R);
         const uint32_t sbase = smem_u32(ring + (size_t)s * SLOT);
         const uint32_t wbase = sbase + S_CHUNK * 4;
-        const uint32_t acc = tmem_d + (uint32_t)set * 256;
+        const uint32_t acc = tmem_d + (uint32_t)set * 128;
         constexpr uint32_t lbo_a = BPT * 16, lbo_b = R0 * 16, sbo_b = W_BLOCK * 4, w_lo = KC4 * R0 * 16;
 #pragma unroll
         for (int ks = 0; ks < KCH / 8; ++ks) {
@@ -299,9 +304,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
           const uint64_t al = make_desc(sbase + S_HALF * 4 + ks * 2 * lbo_a, lbo_a, 128);
           const uint64_t bh = make_desc(wbase + ks * 2 * lbo_b, lbo_b, sbo_b);
           const uint64_t bl = make_desc(wbase + w_lo + ks * 2 * lbo_b, lbo_b, sbo_b);
-          mma_tf32(acc + (ks & 1) * 64, ah, bh, idesc, (uint32_t)(ks >= 2));     // hi*hi: two accumulators in turn
-          mma_tf32(acc + 128, ah, bl, idesc, (uint32_t)(ks > 0));                  // cross terms: third accumulator
-          mma_tf32(acc + 128, al, bh, idesc, 1);
+          mma_tf32(acc, ah, bh, idesc, (uint32_t)(ks > 0));          // hi*hi: a chain of 8
+          mma_tf32(acc + 64, ah, bl, idesc, (uint32_t)(ks > 0));     // cross terms: second accumulator, chain of 16
+          mma_tf32(acc + 64, al, bh, idesc, 1);
         }
         mma_commit(&bar_empty[s]);
         mma_commit(&bar_acc_full[set]);
@@ -402,16 +407,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
 #pragma unroll
         for (int i = 0; i < 32; ++i) racc[i] = 0.f;
         for (int c = 0; c < njs; ++c, ++qe) {
-          const int set = (int)(qe & 1);
-          mbar_wait(&bar_acc_full[set], (uint32_t)((qe / 2) & 1));
+          const int set = (int)(qe % NSET);
+          if (lane == 0) mbar_wait(&bar_acc_full[set], (uint32_t)((qe / NSET) & 1));
+          __syncwarp();
           tc_fence_after();
 #ifdef GNAS_RHN_TIMING
           { const int t_mark = t; if (tid == 0 && c == (stage == 0 ? nch : 0)) RTC_MARK(stage, 0); }
 #endif
           if (32 * hf < R) {
-            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(set * 256 + 32 * hf);
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(set * 128 + 32 * hf);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
+            for (int a = 0; a < 2; ++a) {
               float v[32];
               tmem_ld32(taddr + a * 64, v);
 #pragma unroll
@@ -511,7 +517,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
 }
 
 static inline size_t smem_bytes() {
-  return sizeof(float) * ((size_t)NSLOT * SLOT + RMAX * PITCH + 36 * 4 + 36 + 2 * 8 * NC + 4) + 8 * (2 * NSLOT + 4) + 16;
+  return sizeof(float) * ((size_t)NSLOT * SLOT + RMAX * PITCH + 36 * 4 + 36 + 2 * 8 * NC + 4) + 8 * (2 * NSLOT + 2 * NSET) + 16;
 }
 
 }  // namespace rtc
