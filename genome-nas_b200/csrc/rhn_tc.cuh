@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
   }
   if (warp == 0) tmem_alloc(tmem_slot, TM_COLS);
   if (tid == 32) {
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 3); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(&bar_full[i], 2); mbar_init(&bar_empty[i], 1); }
     for (int i = 0; i < NSET; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 8); }
     mbar_fence_init();
   }
@@ -254,28 +254,25 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
       }
     }
   } else if (warp >= 10) {
-    // ================= weight loaders (2 warps): the 8 - j leading blocks of the chunk are one contiguous range;
-    // cp.async 16 bytes per lane, one group per job, the previous job's group is handed over while this one flies
-    const int lw = warp - 10;
-    for (long long q = 0; q <= njobs; ++q) {
-      if (q < njobs) {
-        const int s = (int)(q % NSLOT);
-        const Job j = job_of(q, nch);
-        if (q >= NSLOT && lane == 0) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
-        __syncwarp();
-        const float* src = j.stage == 0 ? wp + (long long)j.chunk * W_BLOCK
-                                        : wp + 2LL * nch * W_BLOCK + (long long)j.chunk * 8 * W_BLOCK;
-        const int pieces = (j.stage == 0 ? 1 : 9 - j.stage) * (W_BLOCK / 4);      // 16-byte pieces
-        float* dst = ring + (size_t)s * SLOT + S_CHUNK;
-        for (int idx = lw * 32 + lane; idx < pieces; idx += 64) cp_async16(dst + (size_t)idx * 4, src + (size_t)idx * 4);
-      }
+    // ================= weight loaders (2 warps, alternating chunks): the 8 - j leading blocks of the chunk are one
+    // contiguous range; cp.async 16 bytes per lane, then wait for the own group, fence for the async proxy (the
+    // tensor core reads shared memory through it) and hand the slot over.  A loader never waits for anything but
+    // its slot, so the hand-over of a chunk does not depend on later chunks.
+    for (long long q = warp - 10; q < njobs; q += 2) {
+      const int s = (int)(q % NSLOT);
+      const Job j = job_of(q, nch);
+      if (q >= NSLOT && lane == 0) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
+      __syncwarp();
+      const float* src = j.stage == 0 ? wp + (long long)j.chunk * W_BLOCK
+                                      : wp + 2LL * nch * W_BLOCK + (long long)j.chunk * 8 * W_BLOCK;
+      const int pieces = (j.stage == 0 ? 1 : 9 - j.stage) * (W_BLOCK / 4);      // 16-byte pieces
+      float* dst = ring + (size_t)s * SLOT + S_CHUNK;
+      for (int idx = lane; idx < pieces; idx += 32) cp_async16(dst + (size_t)idx * 4, src + (size_t)idx * 4);
       cp_async_commit();
-      if (q >= 1) {
-        cp_async_wait<1>();
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_full[(q - 1) % NSLOT]);
-      }
+      cp_async_wait<0>();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[s]);
     }
   } else if (warp == 9) {
     // ================= MMA issuer: every chunk starts fresh accumulators in set q % NSET
