@@ -12,9 +12,9 @@
 // tf32 hi + lo and three products (hi*hi, hi*lo, lo*hi) accumulate in fp32 in tensor memory.  The tensor core
 // TRUNCATES when it adds into the accumulator; in a 378-stage recurrence that bias does not average out (one
 // 64-step chain per stage: output error 2.1e-5 at T = 42 against 5.9e-6 for fp32 FFMA, measured and reproduced
-// by a truncation model).  So the chains are kept to ONE 64-column K chunk (8 hi*hi products in one accumulator,
-// the 16 cross terms in a second), and the epilogue warps drain every chunk into fp32 registers (round-to-nearest
-// adds) while the next chunks multiply into the other three accumulator sets: fp32-class error in the model.
+// by a truncation model).  So the chains are kept to ONE 64-column K chunk (8 products in each of three
+// accumulators: hi*hi, hi*lo, lo*hi), and the epilogue warps drain every chunk into fp32 registers (round-to-
+// nearest adds) while the next chunk multiplies into the second accumulator set: fp32-class error in the model.
 // Measured on a B200 (tools/umma_probe.cu): an M = 64 instruction costs 27 cycles for N <= 32 and 33 for N = 64
 // (the shared-memory read of A), so the batch is the M side.
 //
@@ -54,8 +54,8 @@ constexpr int SLOT = S_CHUNK + W_CHUNK_MAX;          // floats per ring slot (64
 constexpr int PITCH = 72;                // part[column][batch] pitch: conflict-free for the dump and for (batch, column) readers
 constexpr int EPI = 256;                 // epilogue threads: (batch row m = tid / 4, column = tid % 4)
 constexpr int THREADS = EPI + 128;           // + state producer, MMA issuer, two weight-loader warps
-constexpr int NSET = 4;                  // accumulator sets in tensor memory: {hi*hi, cross terms} x 64 columns each
-constexpr int TM_COLS = NSET * 128;
+constexpr int NSET = 2;                  // accumulator sets in tensor memory: {hi*hi, hi*lo, lo*hi} x 64 columns, pitch 256
+constexpr int TM_COLS = NSET * 256;
 
 struct Plan {
   int nch;                               // K chunks per H
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
         const uint32_t idesc = make_idesc_mn(64, R);
         const uint32_t sbase = smem_u32(ring + (size_t)s * SLOT);
         const uint32_t wbase = sbase + S_CHUNK * 4;
-        const uint32_t acc = tmem_d + (uint32_t)set * 128;
+        const uint32_t acc = tmem_d + (uint32_t)set * 256;
         constexpr uint32_t lbo_a = BPT * 16, lbo_b = R0 * 16, sbo_b = W_BLOCK * 4, w_lo = KC4 * R0 * 16;
 #pragma unroll
         for (int ks = 0; ks < KCH / 8; ++ks) {
@@ -301,9 +301,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
           const uint64_t al = make_desc(sbase + S_HALF * 4 + ks * 2 * lbo_a, lbo_a, 128);
           const uint64_t bh = make_desc(wbase + ks * 2 * lbo_b, lbo_b, sbo_b);
           const uint64_t bl = make_desc(wbase + w_lo + ks * 2 * lbo_b, lbo_b, sbo_b);
-          mma_tf32(acc, ah, bh, idesc, (uint32_t)(ks > 0));          // hi*hi: a chain of 8
-          mma_tf32(acc + 64, ah, bl, idesc, (uint32_t)(ks > 0));     // cross terms: second accumulator, chain of 16
-          mma_tf32(acc + 64, al, bh, idesc, 1);
+          // three accumulators in turn: back-to-back MMAs into the SAME accumulator serialise on its latency
+          // (measured: ~200 cycles per K step with the two cross terms in one accumulator, ~100 with three)
+          mma_tf32(acc, ah, bh, idesc, (uint32_t)(ks > 0));
+          mma_tf32(acc + 64, ah, bl, idesc, (uint32_t)(ks > 0));
+          mma_tf32(acc + 128, al, bh, idesc, (uint32_t)(ks > 0));
         }
         mma_commit(&bar_empty[s]);
         mma_commit(&bar_acc_full[set]);
@@ -412,9 +414,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
           { const int t_mark = t; if (tid == 0 && c == (stage == 0 ? nch : 0)) RTC_MARK(stage, 0); }
 #endif
           if (32 * hf < R) {
-            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(set * 128 + 32 * hf);
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(set * 256 + 32 * hf);
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
+            for (int a = 0; a < 3; ++a) {
               float v[32];
               tmem_ld32(taddr + a * 64, v);
 #pragma unroll
