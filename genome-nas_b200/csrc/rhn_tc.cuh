@@ -56,6 +56,7 @@ constexpr int EPI = 256;                 // epilogue threads: (batch row m = tid
 constexpr int THREADS = EPI + 128;           // + state producer, MMA issuer, two weight-loader warps
 constexpr int NSET = 2;                  // accumulator sets in tensor memory: {hi*hi, hi*lo, lo*hi} x 64 columns, pitch 256
 constexpr int TM_COLS = NSET * 256;
+static_assert(NSET == 2, "the set / parity arithmetic below assumes two accumulator sets");
 
 struct Plan {
   int nch;                               // K chunks per H
@@ -145,16 +146,27 @@ struct Fwd {
 };
 
 struct Job { int t, stage, chunk, first, last; };     // chunk: index inside the stage
-// jobs of a time step: stage 0 = 2 nch chunks (x then h), stages 1..8 = nch chunks each
-__device__ __forceinline__ Job job_of(long long q, int nch) {
-  const int per_t = 10 * nch;
+// Jobs (chunks) in issue order: per time step, stage 0 = 2 nch chunks (x then h), stages 1..8 = nch chunks each.
+// Every role walks the same sequence with this cursor: no divisions in the single-thread loops (a 64-bit
+// division per chunk cost the MMA warp ~400 cycles), ring slot / phase kept incrementally.
+struct Cursor {
+  int nch, slot, round;        // ring slot of the job and how often the ring has wrapped
+  long long q;
   Job j;
-  j.t = (int)(q / per_t);
-  const int r = (int)(q - (long long)j.t * per_t);
-  if (r < 2 * nch) { j.stage = 0; j.chunk = r; j.first = r == 0; j.last = r == 2 * nch - 1; }
-  else { j.stage = 1 + (r - 2 * nch) / nch; j.chunk = (r - 2 * nch) % nch; j.first = j.chunk == 0; j.last = j.chunk == nch - 1; }
-  return j;
-}
+  __device__ __forceinline__ explicit Cursor(int nch_) : nch(nch_), slot(0), round(0), q(0) {
+    j.t = 0; j.stage = 0; j.chunk = 0; j.first = 1; j.last = 2 * nch_ == 1;
+  }
+  __device__ __forceinline__ void next() {
+    const int n = j.stage == 0 ? 2 * nch : nch;
+    if (++j.chunk == n) { j.chunk = 0; if (++j.stage == 9) { j.stage = 0; ++j.t; } }
+    j.first = j.chunk == 0;
+    j.last = j.chunk == (j.stage == 0 ? 2 * nch : nch) - 1;
+    if (++slot == NSLOT) { slot = 0; ++round; }
+    ++q;
+  }
+  __device__ __forceinline__ uint32_t full_parity() const { return (uint32_t)(round & 1); }          // this use of the slot
+  __device__ __forceinline__ uint32_t prev_parity() const { return (uint32_t)((round - 1) & 1); }    // the use before it
+};
 __device__ __forceinline__ int rows_of(int stage) { return stage == 0 ? R0 : R0 * (9 - stage); }
 
 __device__ __forceinline__ void spin_until(const unsigned* bar, unsigned target) {
@@ -229,10 +241,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
   if (warp == 8) {
     // ================= state producer: one lane; TMA bulk copy of a 32 KB operand chunk per job
     if (lane == 0) {
-      for (long long q = 0; q < njobs; ++q) {
-        const int s = (int)(q % NSLOT);
-        const Job j = job_of(q, nch);
-        if (q >= NSLOT) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
+      for (Cursor cu(nch); cu.q < njobs; cu.next()) {
+        const int s = cu.slot;
+        const Job j = cu.j;
+        if (cu.round > 0) mbar_wait(&bar_empty[s], cu.prev_parity());
         const float* src;
         if (j.stage == 0 && j.chunk < nch) src = P.xc + ((long long)j.t * nch + j.chunk) * S_CHUNK;
         else {
@@ -258,10 +270,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
     // contiguous range; cp.async 16 bytes per lane, then wait for the own group, fence for the async proxy (the
     // tensor core reads shared memory through it) and hand the slot over.  A loader never waits for anything but
     // its slot, so the hand-over of a chunk does not depend on later chunks.
-    for (long long q = warp - 10; q < njobs; q += 2) {
-      const int s = (int)(q % NSLOT);
-      const Job j = job_of(q, nch);
-      if (q >= NSLOT && lane == 0) mbar_wait(&bar_empty[s], (uint32_t)((q / NSLOT - 1) & 1));
+    Cursor cu(nch);
+    if (warp == 11 && njobs > 1) cu.next();
+    for (; cu.q < njobs; cu.next(), cu.next()) {
+      const int s = cu.slot;
+      const Job j = cu.j;
+      if (cu.round > 0 && lane == 0) mbar_wait(&bar_empty[s], cu.prev_parity());
       __syncwarp();
       const float* src = j.stage == 0 ? wp + (long long)j.chunk * W_BLOCK
                                       : wp + 2LL * nch * W_BLOCK + (long long)j.chunk * 8 * W_BLOCK;
@@ -276,13 +290,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
     }
   } else if (warp == 9) {
     // ================= MMA issuer: every chunk starts fresh accumulators in set q % NSET
-    for (long long q = 0; q < njobs; ++q) {
-      const int s = (int)(q % NSLOT), set = (int)(q % NSET);
-      const Job j = job_of(q, nch);
+    for (Cursor cu(nch); cu.q < njobs; cu.next()) {
+      const long long q = cu.q;
+      const int s = cu.slot, set = (int)(q & (NSET - 1));
+      const Job j = cu.j;
       const int R = rows_of(j.stage);
       if (lane == 0) {            // one lane polls (32 pollers on one mbarrier only slow the arrivals down)
-        if (q >= NSET) mbar_wait(&bar_acc_empty[set], (uint32_t)((q / NSET - 1) & 1));
-        mbar_wait(&bar_full[s], (uint32_t)((q / NSLOT) & 1));
+        if (q >= NSET) mbar_wait(&bar_acc_empty[set], (uint32_t)(((q >> 1) - 1) & 1));
+#ifdef GNAS_RHN_TIMING
+        if (blockIdx.x == 0 && j.t == 1 && j.stage == 1) dbg[72 + j.chunk * 5 + 0] = clock64();
+#endif
+        mbar_wait(&bar_full[s], cu.full_parity());
+#ifdef GNAS_RHN_TIMING
+        if (blockIdx.x == 0 && j.t == 1 && j.stage == 1) dbg[72 + j.chunk * 5 + 1] = clock64();
+#endif
       }
       __syncwarp();
       tc_fence_after();
@@ -295,22 +316,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
         const uint32_t wbase = sbase + S_CHUNK * 4;
         const uint32_t acc = tmem_d + (uint32_t)set * 256;
         constexpr uint32_t lbo_a = BPT * 16, lbo_b = R0 * 16, sbo_b = W_BLOCK * 4, w_lo = KC4 * R0 * 16;
+        // descriptors differ only in the start-address field (bits 0..13, units of 16 bytes): build the four bases
+        // once per chunk and step them with plain adds -- the single issuing thread is latency-bound, every
+        // instruction between two MMAs shows (measured: 53 cycles per MMA with make_desc inside the loop)
+        const uint64_t a_hi = make_desc(sbase, lbo_a, 128), a_lo = a_hi + (uint64_t)((S_HALF * 4) >> 4);
+        const uint64_t b_hi = make_desc(wbase, lbo_b, sbo_b), b_lo = b_hi + (uint64_t)(w_lo >> 4);
 #pragma unroll
         for (int ks = 0; ks < KCH / 8; ++ks) {
-          const uint64_t ah = make_desc(sbase + ks * 2 * lbo_a, lbo_a, 128);
-          const uint64_t al = make_desc(sbase + S_HALF * 4 + ks * 2 * lbo_a, lbo_a, 128);
-          const uint64_t bh = make_desc(wbase + ks * 2 * lbo_b, lbo_b, sbo_b);
-          const uint64_t bl = make_desc(wbase + w_lo + ks * 2 * lbo_b, lbo_b, sbo_b);
-          // three accumulators in turn: back-to-back MMAs into the SAME accumulator serialise on its latency
-          // (measured: ~200 cycles per K step with the two cross terms in one accumulator, ~100 with three)
-          mma_tf32(acc, ah, bh, idesc, (uint32_t)(ks > 0));
-          mma_tf32(acc + 64, ah, bl, idesc, (uint32_t)(ks > 0));
-          mma_tf32(acc + 128, al, bh, idesc, (uint32_t)(ks > 0));
+          const uint64_t ka = (uint64_t)(ks * ((2 * lbo_a) >> 4)), kb = (uint64_t)(ks * ((2 * lbo_b) >> 4));
+          // three accumulators in turn: back-to-back MMAs into the SAME accumulator would serialise on its latency
+          mma_tf32(acc, a_hi + ka, b_hi + kb, idesc, (uint32_t)(ks > 0));
+          mma_tf32(acc + 64, a_hi + ka, b_lo + kb, idesc, (uint32_t)(ks > 0));
+          mma_tf32(acc + 128, a_lo + ka, b_hi + kb, idesc, (uint32_t)(ks > 0));
         }
         mma_commit(&bar_empty[s]);
         mma_commit(&bar_acc_full[set]);
 #ifdef GNAS_RHN_TIMING
         { const int t_mark = j.t; if (j.last) RTC_MARK(j.stage, 6); }
+        if (blockIdx.x == 0 && j.t == 1 && j.stage == 1) dbg[72 + j.chunk * 5 + 2] = clock64();
 #endif
       }
       __syncwarp();
@@ -406,12 +429,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
 #pragma unroll
         for (int i = 0; i < 32; ++i) racc[i] = 0.f;
         for (int c = 0; c < njs; ++c, ++qe) {
-          const int set = (int)(qe % NSET);
-          if (lane == 0) mbar_wait(&bar_acc_full[set], (uint32_t)((qe / NSET) & 1));
+          const int set = (int)(qe & (NSET - 1));
+          if (lane == 0) mbar_wait(&bar_acc_full[set], (uint32_t)((qe >> 1) & 1));
           __syncwarp();
           tc_fence_after();
 #ifdef GNAS_RHN_TIMING
           { const int t_mark = t; if (tid == 0 && c == (stage == 0 ? nch : 0)) RTC_MARK(stage, 0); }
+          if (blockIdx.x == 0 && t == 1 && stage == 1 && tid == 0) dbg[72 + c * 5 + 3] = clock64();
 #endif
           if (32 * hf < R) {
             const uint32_t taddr = tmem_d + ((uint32_t)(32 * q4) << 16) + (uint32_t)(set * 256 + 32 * hf);
@@ -426,6 +450,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_acc_empty[set]);
+#ifdef GNAS_RHN_TIMING
+          if (blockIdx.x == 0 && t == 1 && stage == 1 && tid == 0) dbg[72 + c * 5 + 4] = clock64();
+#endif
         }
         if (32 * hf < R && lane < 16) {
 #pragma unroll

@@ -57,6 +57,12 @@ if os.environ.get("GNAS_RHN_TC", "1") != "0":
         prev_pub = v[2]
         print(line)
     print("time step cycles (published stage 8 - barrier stage 0):", int(marks[8, 2]) - base)
+    ch = ws[bar_off + 16 + 72 * 2: bar_off + 16 + (72 + 40) * 2].view(torch.int64).cpu().view(8, 5)
+    b1 = int(marks[1, 4])
+    print("stage 1 chunks [cycles after the stage's barrier release]: mma: acc-empty ok | operands ok | issued ;  epilogue warp 0: acc-full seen | drained")
+    for c in range(8):
+        v = [int(ch[c, k]) - b1 for k in range(5)]
+        print(f"  chunk {c}: {v[0]:7d} {v[1]:7d} {v[2]:7d}   {v[3]:7d} {v[4]:7d}")
 else:
     marks = ws[bar_off + 16: bar_off + 16 + 9 * 4 * 2].view(torch.int64).cpu().view(9, 4)
     base = int(marks[0, 0])
