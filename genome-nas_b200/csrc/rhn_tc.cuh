@@ -25,9 +25,10 @@
 // rows][4]: SBO = one block, LBO = 128 bytes), so the 8 (8 - j) rows stage j needs are one contiguous range.
 // BatchNorm over the batch is per column, hence CTA-local; a grid barrier separates stages.
 //
-// Warp roles (384 threads): warps 0-7 epilogue (TMEM -> registers -> shared, gates, BatchNorm, publish, stash for
-// backward), warp 8 state producer (grid-barrier wait + TMA), warp 9 MMA issuer (one elected lane), warps 10-11
-// weight loaders (cp.async: a 1-D bulk copy costs ~600 cycles of the TMA unit whatever its size -- measured, two
+// Warp roles (416 threads): warps 0-7 epilogue (TMEM -> registers -> shared, gates, BatchNorm, publish, stash for
+// backward), warp 8 state producer (grid-barrier wait + TMA), warps 9 and 12 MMA issuers (one elected lane each;
+// they alternate chunks and own one accumulator set each, so the barrier polls and bookkeeping of one overlap the
+// issue of the other -- a single issuing thread is latency-bound), warps 10-11 weight loaders (cp.async: a 1-D bulk copy costs ~600 cycles of the TMA unit whatever its size -- measured, two
 // per chunk made the unit the bottleneck -- so only the state goes through it).
 // The same source is compiled for the CPU emulator against a functional model of mbarrier / bulk copy / tcgen05
 // (tests/emul/tc_emul.h), which is how the layouts and hand-offs are tested without a GPU.
@@ -53,7 +54,7 @@ constexpr int W_CHUNK_MAX = 8 * W_BLOCK;
 constexpr int SLOT = S_CHUNK + W_CHUNK_MAX;          // floats per ring slot (64 KB)
 constexpr int PITCH = 72;                // part[column][batch] pitch: conflict-free for the dump and for (batch, column) readers
 constexpr int EPI = 256;                 // epilogue threads: (batch row m = tid / 4, column = tid % 4)
-constexpr int THREADS = EPI + 128;           // + state producer, MMA issuer, two weight-loader warps
+constexpr int THREADS = EPI + 160;           // + state producer, two MMA issuers, two weight-loader warps
 constexpr int NSET = 2;                  // accumulator sets in tensor memory: {hi*hi, hi*lo, lo*hi} x 64 columns, pitch 256
 constexpr int TM_COLS = NSET * 256;
 static_assert(NSET == 2, "the set / parity arithmetic below assumes two accumulator sets");
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
         bulk_g2s(ring + (size_t)s * SLOT, src, S_CHUNK * 4, &bar_full[s]);
       }
     }
-  } else if (warp >= 10) {
+  } else if (warp == 10 || warp == 11) {
     // ================= weight loaders (2 warps, alternating chunks): the 8 - j leading blocks of the chunk are one
     // contiguous range; cp.async 16 bytes per lane, then wait for the own group, fence for the async proxy (the
     // tensor core reads shared memory through it) and hand the slot over.  A loader never waits for anything but
@@ -288,9 +289,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[s]);
     }
-  } else if (warp == 9) {
-    // ================= MMA issuer: every chunk starts fresh accumulators in set q % NSET
-    for (Cursor cu(nch); cu.q < njobs; cu.next()) {
+  } else if (warp == 9 || warp == 12) {
+    // ================= MMA issuers: warp 9 takes the even chunks (accumulator set 0), warp 12 the odd ones (set 1);
+    // every chunk starts fresh accumulators
+    Cursor cu(nch);
+    if (warp == 12 && njobs > 1) cu.next();
+    for (; cu.q < njobs; cu.next(), cu.next()) {
       const long long q = cu.q;
       const int s = cu.slot, set = (int)(q & (NSET - 1));
       const Job j = cu.j;
