@@ -45,6 +45,7 @@ constexpr int BPT = 64;                  // batch rows of the MMA (padded)
 constexpr int KCH = 64;                  // K per pipeline chunk
 constexpr int KC4 = KCH / 4;             // 4-column groups (core-matrix columns) per chunk
 constexpr int NSLOT = 3;
+constexpr int GRP = 2;                   // chunks multiplied into one accumulator set before it is drained (power of two)
 constexpr int S_HALF = KC4 * BPT * 4;    // floats of the hi (or lo) half of a state chunk (16 KB)
 constexpr int S_CHUNK = 2 * S_HALF;      // 32 KB
 constexpr int R0 = 2 * NC;               // output columns of one weight matrix per CTA (c | h)
@@ -146,22 +147,27 @@ struct Fwd {
   RhnTable tb;
 };
 
-struct Job { int t, stage, chunk, first, last; };     // chunk: index inside the stage
+struct Job { int t, stage, chunk, first, last, gfirst, glast; };     // chunk: index inside the stage; g*: accumulator group
 // Jobs (chunks) in issue order: per time step, stage 0 = 2 nch chunks (x then h), stages 1..8 = nch chunks each.
 // Every role walks the same sequence with this cursor: no divisions in the single-thread loops (a 64-bit
 // division per chunk cost the MMA warp ~400 cycles), ring slot / phase kept incrementally.
 struct Cursor {
   int nch, slot, round;        // ring slot of the job and how often the ring has wrapped
+  int g;                       // accumulator group of the job (GRP consecutive chunks of one stage)
   long long q;
   Job j;
-  __device__ __forceinline__ explicit Cursor(int nch_) : nch(nch_), slot(0), round(0), q(0) {
+  __device__ __forceinline__ explicit Cursor(int nch_) : nch(nch_), slot(0), round(0), g(0), q(0) {
     j.t = 0; j.stage = 0; j.chunk = 0; j.first = 1; j.last = 2 * nch_ == 1;
+    j.gfirst = 1; j.glast = GRP == 1 || j.last;
   }
   __device__ __forceinline__ void next() {
+    if (j.glast) ++g;
     const int n = j.stage == 0 ? 2 * nch : nch;
     if (++j.chunk == n) { j.chunk = 0; if (++j.stage == 9) { j.stage = 0; ++j.t; } }
     j.first = j.chunk == 0;
     j.last = j.chunk == (j.stage == 0 ? 2 * nch : nch) - 1;
+    j.gfirst = (j.chunk & (GRP - 1)) == 0;
+    j.glast = (j.chunk & (GRP - 1)) == GRP - 1 || j.last;
     if (++slot == NSLOT) { slot = 0; ++round; }
     ++q;
   }
@@ -292,15 +298,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
   } else if (warp == 9 || warp == 12) {
     // ================= MMA issuers: warp 9 takes the even chunks (accumulator set 0), warp 12 the odd ones (set 1);
     // every chunk starts fresh accumulators
-    Cursor cu(nch);
-    if (warp == 12 && njobs > 1) cu.next();
-    for (; cu.q < njobs; cu.next(), cu.next()) {
+    const int mine = warp == 9 ? 0 : 1;
+    for (Cursor cu(nch); cu.q < njobs; cu.next()) {
+      if ((cu.g & 1) != mine) continue;
       const long long q = cu.q;
-      const int s = cu.slot, set = (int)(q & (NSET - 1));
+      const int s = cu.slot, set = cu.g & 1;
       const Job j = cu.j;
       const int R = rows_of(j.stage);
       if (lane == 0) {            // one lane polls (32 pollers on one mbarrier only slow the arrivals down)
-        if (q >= NSET) mbar_wait(&bar_acc_empty[set], (uint32_t)(((q >> 1) - 1) & 1));
+        if (j.gfirst && cu.g >= NSET) mbar_wait(&bar_acc_empty[set], (uint32_t)(((cu.g >> 1) - 1) & 1));
 #ifdef GNAS_RHN_TIMING
         if (blockIdx.x == 0 && j.t == 1 && j.stage == 1) dbg[72 + j.chunk * 5 + 0] = clock64();
 #endif
@@ -329,12 +335,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
         for (int ks = 0; ks < KCH / 8; ++ks) {
           const uint64_t ka = (uint64_t)(ks * ((2 * lbo_a) >> 4)), kb = (uint64_t)(ks * ((2 * lbo_b) >> 4));
           // three accumulators in turn: back-to-back MMAs into the SAME accumulator would serialise on its latency
-          mma_tf32(acc, a_hi + ka, b_hi + kb, idesc, (uint32_t)(ks > 0));
-          mma_tf32(acc + 64, a_hi + ka, b_lo + kb, idesc, (uint32_t)(ks > 0));
-          mma_tf32(acc + 128, a_lo + ka, b_hi + kb, idesc, (uint32_t)(ks > 0));
+          const uint32_t accf = (uint32_t)(ks > 0 || !j.gfirst);     // fresh accumulators at the first K step of a group
+          mma_tf32(acc, a_hi + ka, b_hi + kb, idesc, accf);
+          mma_tf32(acc + 64, a_hi + ka, b_lo + kb, idesc, accf);
+          mma_tf32(acc + 128, a_lo + ka, b_hi + kb, idesc, accf);
         }
         mma_commit(&bar_empty[s]);
-        mma_commit(&bar_acc_full[set]);
+        if (j.glast) mma_commit(&bar_acc_full[set]);
 #ifdef GNAS_RHN_TIMING
         { const int t_mark = j.t; if (j.last) RTC_MARK(j.stage, 6); }
         if (blockIdx.x == 0 && j.t == 1 && j.stage == 1) dbg[72 + j.chunk * 5 + 2] = clock64();
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
       return q * sj + g * (F - q * sj);
     };
 
-    long long qe = 0;                                   // chunk (job) counter, same order as the MMA warp
+    long long ge = 0;                                   // accumulator-group counter, same order as the MMA warps
     for (int t = 0; t < T; ++t) {
       for (int stage = 0; stage < 9; ++stage) {
         const int R = rows_of(stage);
@@ -432,9 +439,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
         float racc[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) racc[i] = 0.f;
-        for (int c = 0; c < njs; ++c, ++qe) {
-          const int set = (int)(qe & (NSET - 1));
-          if (lane == 0) mbar_wait(&bar_acc_full[set], (uint32_t)((qe >> 1) & 1));
+        for (int c = 0; c < njs; c += GRP, ++ge) {
+          const int set = (int)(ge & 1);
+          if (lane == 0) mbar_wait(&bar_acc_full[set], (uint32_t)((ge >> 1) & 1));
           __syncwarp();
           tc_fence_after();
 #ifdef GNAS_RHN_TIMING
