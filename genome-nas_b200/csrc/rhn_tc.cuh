@@ -25,10 +25,10 @@
 // rows][4]: SBO = one block, LBO = 128 bytes), so the 8 (8 - j) rows stage j needs are one contiguous range.
 // BatchNorm over the batch is per column, hence CTA-local; a grid barrier separates stages.
 //
-// Warp roles (416 threads): warps 0-7 epilogue (TMEM -> registers -> shared, gates, BatchNorm, publish, stash for
-// backward), warp 8 state producer (grid-barrier wait + TMA), warps 9 and 12 MMA issuers (one elected lane each;
-// they alternate chunks and own one accumulator set each, so the barrier polls and bookkeeping of one overlap the
-// issue of the other -- a single issuing thread is latency-bound), warps 10-11 weight loaders (cp.async: a 1-D bulk copy costs ~600 cycles of the TMA unit whatever its size -- measured, two
+// Warp roles (448 threads): warps 0-7 epilogue (TMEM -> registers -> shared, gates, BatchNorm, publish, stash for
+// backward), warp 8 state producer (grid-barrier wait + TMA), warps 9 and 10 MMA issuers (one elected lane each;
+// they alternate accumulator groups and own one accumulator set each, so the barrier polls and bookkeeping of one
+// overlap the issue of the other -- a single issuing thread is latency-bound), warps 11-13 weight loaders (cp.async: a 1-D bulk copy costs ~600 cycles of the TMA unit whatever its size -- measured, two
 // per chunk made the unit the bottleneck -- so only the state goes through it).
 // The same source is compiled for the CPU emulator against a functional model of mbarrier / bulk copy / tcgen05
 // (tests/emul/tc_emul.h), which is how the layouts and hand-offs are tested without a GPU.
@@ -45,7 +45,7 @@ constexpr int BPT = 64;                  // batch rows of the MMA (padded)
 constexpr int KCH = 64;                  // K per pipeline chunk
 constexpr int KC4 = KCH / 4;             // 4-column groups (core-matrix columns) per chunk
 constexpr int NSLOT = 3;
-constexpr int GRP = 2;                   // chunks multiplied into one accumulator set before it is drained (power of two)
+constexpr int GRP = 1;                   // chunks multiplied into one accumulator set before it is drained (power of two)
 constexpr int S_HALF = KC4 * BPT * 4;    // floats of the hi (or lo) half of a state chunk (16 KB)
 constexpr int S_CHUNK = 2 * S_HALF;      // 32 KB
 constexpr int R0 = 2 * NC;               // output columns of one weight matrix per CTA (c | h)
@@ -55,7 +55,9 @@ constexpr int W_CHUNK_MAX = 8 * W_BLOCK;
 constexpr int SLOT = S_CHUNK + W_CHUNK_MAX;          // floats per ring slot (64 KB)
 constexpr int PITCH = 72;                // part[column][batch] pitch: conflict-free for the dump and for (batch, column) readers
 constexpr int EPI = 256;                 // epilogue threads: (batch row m = tid / 4, column = tid % 4)
-constexpr int THREADS = EPI + 160;           // + state producer, two MMA issuers, two weight-loader warps
+constexpr int NLOAD = NSLOT;             // weight-loader warps: loader w owns ring slot w (chunks w, w + 3, ...), so it can
+                                         // never run two mbarrier phases ahead of the consumer (parity aliasing)
+constexpr int THREADS = EPI + 32 * (3 + NLOAD);   // + state producer, two MMA issuers, the weight loaders
 constexpr int NSET = 2;                  // accumulator sets in tensor memory: {hi*hi, hi*lo, lo*hi} x 64 columns, pitch 256
 constexpr int TM_COLS = NSET * 256;
 static_assert(NSET == 2, "the set / parity arithmetic below assumes two accumulator sets");
@@ -272,36 +274,40 @@ __global__ void __launch_bounds__(THREADS, 1) k_rhn_fwd_tc(const __grid_constant
         bulk_g2s(ring + (size_t)s * SLOT, src, S_CHUNK * 4, &bar_full[s]);
       }
     }
-  } else if (warp == 10 || warp == 11) {
-    // ================= weight loaders (2 warps, alternating chunks): the 8 - j leading blocks of the chunk are one
-    // contiguous range; cp.async 16 bytes per lane, then wait for the own group, fence for the async proxy (the
-    // tensor core reads shared memory through it) and hand the slot over.  A loader never waits for anything but
-    // its slot, so the hand-over of a chunk does not depend on later chunks.
+  } else if (warp >= 11) {
+    // ================= weight loaders (NLOAD warps, chunk q goes to loader q % NLOAD): the 8 - j leading blocks of
+    // the chunk are one contiguous range; cp.async 16 bytes per lane, then wait for the own group, fence for the
+    // async proxy (the tensor core reads shared memory through it) and hand the slot over.  A loader never waits
+    // for anything but its slot, so the hand-over of a chunk does not depend on later chunks; one chunk takes a
+    // warp ~2 k cycles (issue + L2 round trip), hence one loader per ring slot.
     Cursor cu(nch);
-    if (warp == 11 && njobs > 1) cu.next();
-    for (; cu.q < njobs; cu.next(), cu.next()) {
+    for (int i = 0; i < warp - 11 && cu.q < njobs; ++i) cu.next();
+    while (cu.q < njobs) {
       const int s = cu.slot;
       const Job j = cu.j;
       if (cu.round > 0 && lane == 0) mbar_wait(&bar_empty[s], cu.prev_parity());
       __syncwarp();
-      const float* src = j.stage == 0 ? wp + (long long)j.chunk * W_BLOCK
-                                      : wp + 2LL * nch * W_BLOCK + (long long)j.chunk * 8 * W_BLOCK;
-      const int pieces = (j.stage == 0 ? 1 : 9 - j.stage) * (W_BLOCK / 4);      // 16-byte pieces
-      float* dst = ring + (size_t)s * SLOT + S_CHUNK;
-      for (int idx = lane; idx < pieces; idx += 32) cp_async16(dst + (size_t)idx * 4, src + (size_t)idx * 4);
+      const float* src = (j.stage == 0 ? wp + (long long)j.chunk * W_BLOCK
+                                       : wp + 2LL * nch * W_BLOCK + (long long)j.chunk * 8 * W_BLOCK) + lane * 4;
+      const int nblk = j.stage == 0 ? 1 : 9 - j.stage;
+      float* dst = ring + (size_t)s * SLOT + S_CHUNK + lane * 4;
+      for (int b = 0; b < nblk; ++b) {
+#pragma unroll
+        for (int i = 0; i < W_BLOCK / 128; ++i) cp_async16(dst + b * W_BLOCK + i * 128, src + b * W_BLOCK + i * 128);
+      }
       cp_async_commit();
       cp_async_wait<0>();
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[s]);
+      for (int i = 0; i < NLOAD && cu.q < njobs; ++i) cu.next();
     }
-  } else if (warp == 9 || warp == 12) {
-    // ================= MMA issuers: warp 9 takes the even chunks (accumulator set 0), warp 12 the odd ones (set 1);
+  } else if (warp == 9 || warp == 10) {
+    // ================= MMA issuers: warp 9 takes the even groups (accumulator set 0), warp 10 the odd ones (set 1);
     // every chunk starts fresh accumulators
     const int mine = warp == 9 ? 0 : 1;
     for (Cursor cu(nch); cu.q < njobs; cu.next()) {
       if ((cu.g & 1) != mine) continue;
-      const long long q = cu.q;
       const int s = cu.slot, set = cu.g & 1;
       const Job j = cu.j;
       const int R = rows_of(j.stage);
