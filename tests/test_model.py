@@ -63,11 +63,17 @@ def check_forward_backward(g, device, monkeypatch):
         ref = gn[n]
         if ref < 1e-12 * total:
             continue
-        # per-tensor rel-L2 against fp64, graded against the reference's own fp32 run: the north
+        # per-tensor rel-L2 against fp64, graded against the reference's own fp32 runs: the north
         # star's 1e-3, or 1.5x the error the reference itself makes on that tensor.  BN statistics are summed in
         # double from the per-warp partials on, so the forward pass (and with it every ReLU / max-pool decision)
-        # is reproducible run to run.
-        lim = max(1e-3, 1.5 * r32[n])
+        # is reproducible run to run.  The full-size goldens hold the reference's fp32 error for BOTH of its CPU
+        # convolution backends (oracle/ref_backend_spread.py: oneDNN on / off): they differ from each other by a
+        # median factor of 2.5 per tensor (p90 6, max 22), i.e. one backend of the reference fails the 1.5x bar of
+        # the other on 81 % of the tensors -- individual ReLU decisions sit within fp32 rounding of their
+        # threshold and flip between any two correct fp32 implementations.  The bar is therefore 1.5x the larger
+        # of the two.
+        rb = g.get("ref32b_err")
+        lim = max(1e-3, 1.5 * (max(rb["onednn"][n], rb["native"][n]) if rb else r32[n]))
         if n in g["grad64"]:
             score[n] = relerr(p.grad, g["grad64"][n]) / lim
         elif "grad_sketch64" in g:
