@@ -11,5 +11,6 @@ from .rnn import DARTSCellSearch  # noqa: F401
 from .model import Genotype, RNNModel, RNNModelSearch  # noqa: F401
 from .architect import Architect  # noqa: F401
 from .train import Hyper, SearchStep, train  # noqa: F401
+from . import mask_supernet  # noqa: F401  (OSP-NAS / Hyperband / random-search mask supernet)
 
 __version__ = "0.1.0"

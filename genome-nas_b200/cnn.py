@@ -34,7 +34,9 @@ _BN_NAMES = {
 }
 
 
-def _fill_edge(desc, region, e, prefix, switch, stride):
+def _fill_edge(desc, region, e, prefix, switch, stride, holder="m_ops", by_index=False):
+    """offsets of one edge's parameters / BN buffers; `holder` and `by_index` select the child naming:
+    `m_ops.<primitive>` (DARTS family) or `_ops.<index>` (mask supernets)"""
     for k, name in enumerate(PRIMITIVES_cnn):
         desc.sw[e][k] = 1 if switch[k] else 0
         for i in range(4):
@@ -43,7 +45,7 @@ def _fill_edge(desc, region, e, prefix, switch, stride):
             desc.bn_off[e][k][i] = -1
         if not switch[k]:
             continue
-        base = f"{prefix}m_ops.{name}."
+        base = f"{prefix}{holder}.{k if by_index else name}."
         if name == 'skip_connect':
             if stride > 1:
                 o1, o2 = region.offsets[base + 'conv_1.weight'], region.offsets[base + 'conv_2.weight']

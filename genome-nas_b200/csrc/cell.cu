@@ -190,7 +190,9 @@ int validate(const GnasCellDesc* d) {
   for (int e = 0; e < d->n_edges; ++e) {
     int n = 0;
     for (int k = 0; k < GNAS_N_PRIMS; ++k) n += d->sw[e][k] ? 1 : 0;
-    if (n != d->n_prims) { set_error("every edge must enable exactly n_prims primitives"); return GNAS_ERR_SHAPE; }
+    // DARTS / P-DARTS / CWP-DARTS enable exactly n_prims per edge; the mask supernets (OSP-NAS, Hyperband, random
+    // search) enable any subset, an edge may even be empty (it then contributes zero)
+    if (n > d->n_prims) { set_error("an edge enables more primitives than the mixing-weight rows have columns"); return GNAS_ERR_SHAPE; }
   }
   return 0;
 }

@@ -409,6 +409,54 @@ def golden_model(tag, cfg, B, seed_params, full=False, pdarts=False):
     print("model", tag, "ok")
 
 
+def golden_mask_supernet():
+    """OSP-NAS / Hyperband mask supernet (randomSearch_and_Hyperband_Tools/model.py, model_search.py): forward +
+    backward of the reference's own classes with a supernet mask and a call-time sub-mask, fp32 and fp64."""
+    from randomSearch_and_Hyperband_Tools import model_search as ref_hb
+    rng = np.random.RandomState(7)
+    sup_n = (rng.rand(14, 9) < 0.6).astype(np.int64); sup_n[:, 0] = 0
+    sup_r = (rng.rand(14, 9) < 0.6).astype(np.int64); sup_r[:, 0] = 0
+    for m in (sup_n, sup_r):
+        for e in range(14):
+            if m[e].sum() == 0:
+                m[e, 1 + rng.randint(8)] = 1
+    sup_w = (rng.rand(36, 5) < 0.6).astype(np.int64); sup_w[:, 0] = 0
+    call_n = sup_n * (rng.rand(14, 9) < 0.7); call_r = sup_r * (rng.rand(14, 9) < 0.7)
+    call_n[3] = 0                                   # an edge with nothing selected contributes zero
+    call_w = sup_w * (rng.rand(36, 5) < 0.8)
+    for r in range(36):                             # every RHN step keeps at least one selected activation
+        if call_w[r].sum() == 0:
+            call_w[r, 1 + rng.randint(4)] = 1
+    seq_len, C, ncls, B = 96, 4, 10, 4
+    res = dict(sup=[sup_n, sup_r, sup_w], call=[call_n.astype(np.int64), call_r.astype(np.int64), call_w.astype(np.int64)],
+               seq_len=seq_len, C=C, num_classes=ncls, B=B, dropouth=0.05, dropoutx=0.1)
+    args = (seq_len, 0.05, 0.1, C, ncls, 6, 4, 4, 3, True, 0.2, None, "TF_bindings", [sup_n, sup_r, sup_w])
+    m0 = ref_hb.RNNModelSearch(*args)
+    shp = shapes_of(m0)
+    P = O.synthetic_params(shp, 61)
+    res["shapes"] = shp
+    xt, yt = O.synthetic_batch(B, seq_len, ncls, 0)
+    for dt, sfx in ((torch.float32, "32"), (torch.float64, "64")):
+        mm = ref_hb.RNNModelSearch(*args)
+        load_into(mm, P)
+        if dt == torch.float64:
+            mm = mm.double()
+        mm.dropout_lin.p = 0.0
+        mm.train()
+        torch.manual_seed(77)
+        logits, hidden, rnn_hs, _ = mm(xt.to(dt), mm.init_hidden(B), res["call"], return_h=True)
+        loss = torch.nn.functional.binary_cross_entropy(logits, yt.to(dt))
+        loss.backward()
+        res["logits" + sfx], res["loss" + sfx] = logits.detach(), loss.detach()
+        res["grad" + sfx] = {n: (p.grad.detach().clone() if p.grad is not None else None) for n, p in mm.named_parameters()}
+        res["state" + sfx] = {k: v.detach().clone() for k, v in mm.state_dict().items() if "running" in k or "tracked" in k}
+    torch.manual_seed(77)
+    res["xm"], res["hm"] = O.draw_rhn_masks(B, 4 * C * 16, 0.1, 0.05)
+    torch.save(res, os.path.join(GOLD, "mask_supernet.pt"))
+    print("mask supernet ok: loss32", float(res["loss32"]), "loss64", float(res["loss64"]),
+          "params with grad", sum(g is not None for g in res["grad64"].values()), "of", len(res["grad64"]))
+
+
 def golden_genotype():
     """Genotypes the reference derives (model_search.py:164-243) from recorded alphas."""
     import json
@@ -486,6 +534,8 @@ def main():
                                switches_reduce=pruned_switches(14, 9, 3, 2),
                                switches_rnn=pruned_switches(36, 5, 2, 3))
         golden_model("tiny_pruned", cfg, 4, 42)
+    if "mask" in todo:
+        golden_mask_supernet()
     if "genotype" in todo:
         golden_genotype()
     if "pdarts3" in todo:
