@@ -409,6 +409,43 @@ def golden_model(tag, cfg, B, seed_params, full=False, pdarts=False):
     print("model", tag, "ok")
 
 
+def golden_unrolled():
+    """Second-order (unrolled) Architect.step of the reference (architect.py:55-129) on the tiny supernet, dropouts
+    off (the four passes of the step would each draw their own RHN masks), fp32 and fp64."""
+    cfg = O.SupernetConfig(seq_len=96, C=4, num_classes=10, dropouth=0.0, dropoutx=0.0)
+    B = 4
+    m0 = build_ref_model(cfg)
+    shp = shapes_of(m0)
+    P = O.synthetic_params(shp, 71)
+    xt, yt = O.synthetic_batch(B, cfg.seq_len, cfg.num_classes, 0)
+    xv, yv = O.synthetic_batch(B, cfg.seq_len, cfg.num_classes, 1)
+    res = dict(cfg=cfg, B=B, shapes=shp, seed_params=71, eta=0.025)
+    for dt, sfx in ((torch.float32, "32"), (torch.float64, "64")):
+        mm = build_ref_model(cfg, P, dt)
+        mm.dropout_lin.p = 0.0
+        mm.train()
+        # the reference's new() builds a fresh fp32 model with the head dropout on (p = 0.1): the copy gets the dtype of
+        # the run and p = 0 (CPU and CUDA draw different masks; the test patches new() of its model the same way)
+        orig_new = mm.new
+
+        def new_nodrop(orig_new=orig_new, dt=dt):
+            m2 = orig_new().to(dt)
+            m2._arch_parameters = [m2.alphas_normal, m2.alphas_reduce, m2.weights]
+            for r in m2.rnns:
+                r.weights = m2.weights
+            m2.dropout_lin.p = 0.0
+            return m2
+        mm.new = new_nodrop
+        opt = torch.optim.SGD(mm.parameters(), lr=res["eta"])
+        arch = RefArchitect(mm, torch.nn.BCELoss(), _Args)
+        torch.manual_seed(5)
+        arch.step(mm.init_hidden(B), xt.to(dt), yt.to(dt), mm.init_hidden(B), xv.to(dt), yv.to(dt), opt, True)
+        res["dalpha" + sfx] = [p.grad.detach().clone() for p in mm.arch_parameters()]
+        res["alpha" + sfx] = [p.detach().clone() for p in mm.arch_parameters()]
+    torch.save(res, os.path.join(GOLD, "unrolled.pt"))
+    print("unrolled ok: fp32 vs fp64 dalpha rel err", [relerr(a, b) for a, b in zip(res["dalpha32"], res["dalpha64"])])
+
+
 def golden_mask_supernet():
     """OSP-NAS / Hyperband mask supernet (randomSearch_and_Hyperband_Tools/model.py, model_search.py): forward +
     backward of the reference's own classes with a supernet mask and a call-time sub-mask, fp32 and fp64."""
@@ -534,6 +571,8 @@ def main():
                                switches_reduce=pruned_switches(14, 9, 3, 2),
                                switches_rnn=pruned_switches(36, 5, 2, 3))
         golden_model("tiny_pruned", cfg, 4, 42)
+    if "unrolled" in todo:
+        golden_unrolled()
     if "mask" in todo:
         golden_mask_supernet()
     if "genotype" in todo:
