@@ -298,7 +298,7 @@ def algorithmic_work(B, sw_normal, sw_reduce, T=42, H=512, n_rnn_edges=36):
     w["rhn_wg"] = rhn
     w["head_fb"] = 2 * 2 * 2.0 * B * (21504 * 925 + 925 * NCLS)
     w["head_wg"] = 2.0 * B * (21504 * 925 + 925 * NCLS)
-    w["head_b"] = 2 * 3 * 4.0 * (21504 * 925 + 925 * NCLS)   # weight read fwd + dx, wgrad write... per pass
+    w["head_f"] = w["head_fb"] + w["head_wg"]                # the five GEMM pairs of the head per step (csrc/head.cu)
     w["optim_b"] = 38035471 * 4.0 * 6                       # sumsq read g; sgd read p, g, m, write p, m
     return w
 
@@ -320,7 +320,7 @@ FAMILIES = [
     ("k_edge_fwd", "", "dw_fwd", "hbm", "dw_fwd_b"), ("k_edge_bwd", "", "dw_bwd", "hbm", "dw_bwd_b"),
     ("k_pool_fwd", "", "pool_fwd", "hbm", "pool_fwd_b"), ("k_pool_bwd", "", "pool_bwd", "hbm", "pool_bwd_b"),
     ("k_mix_fwd", "", "mix_fwd", "hbm", "mix_fwd_b"), ("k_bwd_reduce", "", "bwd_reduce", "hbm", "bwd_reduce_b"),
-    ("k_head", "", "head", "hbm", "head_b"), ("k_sgd", "", "optim", "hbm", "optim_b"), ("k_sumsq", "", "optim", "hbm", "optim_b"),
+    ("k_head", "", "head", "fp32", "head_f"), ("k_sgd", "", "optim", "hbm", "optim_b"), ("k_sumsq", "", "optim", "hbm", "optim_b"),
 ]
 
 

@@ -10,7 +10,8 @@ from .operations import OPS, PRIMITIVES_cnn, PRIMITIVES_rnn  # noqa: F401
 from .rnn import DARTSCellSearch  # noqa: F401
 from .model import Genotype, RNNModel, RNNModelSearch  # noqa: F401
 from .architect import Architect  # noqa: F401
-from .train import Hyper, SearchStep, train  # noqa: F401
+from .train import Hyper, SearchStep, infer, train  # noqa: F401
+from .head import bce_loss, tar_loss  # noqa: F401
 from . import mask_supernet  # noqa: F401  (OSP-NAS / Hyperband / random-search mask supernet)
 
 __version__ = "0.1.0"

@@ -49,6 +49,14 @@ _SIGS = {
     "gnas_rhn_forward": (C.c_int, [C.POINTER(RhnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnas_rhn_backward": (C.c_int, [C.POINTER(RhnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                     C.c_int, _P]),
+    "gnas_head_workspace": (C.c_int, [C.c_int] * 5 + [_I64P, _I64P]),
+    "gnas_head_forward": (C.c_int, [C.c_int] * 6 + [_P] * 9),
+    "gnas_head_backward": (C.c_int, [C.c_int] * 6 + [_P] * 12 + [C.c_int, _P]),
+    "gnas_loss_workspace": (C.c_int, [_I64P]),
+    "gnas_bce_forward": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    "gnas_bce_backward": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "gnas_tar_forward": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, _P]),
+    "gnas_tar_backward": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P]),
     "gnas_grad_sumsq": (C.c_int, [_P, C.c_int64, _P, _P]),
     "gnas_sgd_step": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int, _P, C.c_float, _P]),
     "gnas_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -534,21 +534,39 @@ struct DwBwdJob {
   float* dwd;                        // [C][K] atomics, or null
   int Lin, Lo, tin, omode;
 };
-struct DwBwdBatch { int n, B, C, pad, Wx, Wd, RPW; DwBwdJob j[kMaxDw]; };
+struct DwBwdBatch { int n, B, C, pad, RPW, nseg; DwBwdJob j[kMaxDw]; };
 
-// CTA: channel c, 8 batch rows (one per warp).  Stride 1 (all but the first conv of strided edges): every lane
-// produces 4 consecutive positions from register windows (128-bit shared loads, static tap indices).
+// Tile geometry shared by the kernel and its launcher.  A row [0, Lin) is cut into segments of SEG input positions
+// (a multiple of 4 and of every stride): with whole rows a launch of the C = 8 cells had 1.5 CTAs per SM and every
+// warp walked three dependent phases over 1000 positions -- latency-bound at 9 % of the HBM roofline.
+template <int K, int D, int S>
+struct DwBwdGeom {
+  static constexpr int SEG = S == 1 ? 256 : 252;      // 252 = 4 * 63: a multiple of 2, 3 and 4
+  static constexpr int PADC = (K - 1) * D / 2;
+  // du row: index i <-> l = l0 + i - OFF, OFF a multiple of 4 >= PADC (stride 1) so that windows start 16-byte aligned
+  static constexpr int OFF = S == 1 ? (PADC + 3) / 4 * 4 : K;
+  static constexpr int WX = (SEG + 2 * PADC + 8 + 3) / 4 * 4;                   // x row: index p <-> pos = m0 - pad + p
+  static constexpr int WD = S == 1 ? (SEG + 2 * PADC + 16 + 3) / 4 * 4 : ((SEG + PADC) / S + OFF + 4 + 3) / 4 * 4;
+};
+
+// CTA: channel c, 8 batch rows (one per warp), one segment of SEG input positions.  Stride 1 (all but the first conv
+// of strided edges): every lane produces 4 consecutive positions from register windows (128-bit shared loads, static
+// tap indices).  The staging loops have compile-time bounds: all global loads of a tile are in flight at once.
 template <int K, int D, int S>
 __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwBwdBatch P) {
+  using G = DwBwdGeom<K, D, S>;
+  constexpr int PADC = G::PADC, OFF = G::OFF, SEG = G::SEG, WX = G::WX, WD = G::WD;
+  static_assert(SEG % S == 0 && SEG % 4 == 0, "segment must be a multiple of the stride and of 4");
   const DwBwdJob& J = P.j[blockIdx.z];
   const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // every depthwise candidate of the reference pads by (K-1)*D/2 (operations_14_9.py:24-28)
-  constexpr int PADC = (K - 1) * D / 2;
-  // du row: index i <-> l = i - OFF, OFF a multiple of 4 >= PADC, so that windows start 16-byte aligned
-  constexpr int OFF = S == 1 ? (PADC + 3) / 4 * 4 : K;
+  const int rg = blockIdx.y / P.nseg, seg = blockIdx.y - rg * P.nseg;
+  const int m0 = seg * SEG;                               // first input position of the segment
+  const int m1 = min(J.Lin, m0 + SEG);
+  const int l0 = m0 / S;                                  // du positions l with l*S in [m0, m1)
+  const int l1 = m1 > m0 ? min(J.Lo, (m1 - 1) / S + 1) : l0;
   GNAS_DYN_SMEM(float, smem);
-  float* xrow = smem + warp * (P.Wx + P.Wd);   // T(x) with zero halo: index p <-> pos = p - pad
-  float* drow = xrow + P.Wx;                   // du with zero halo
+  float* xrow = smem + warp * (WX + WD);       // T(x) with zero halo
+  float* drow = xrow + WX;                     // du with zero halo
   __shared__ float red[8][K + 2];
   float mean = 0.f, rstd = 1.f;
   if (J.tin >= T_BN_RELU) { mean = J.in_stat[c]; rstd = J.in_stat[P.C + c]; }
@@ -561,35 +579,47 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
   for (int t = 0; t < K; ++t) gw[t] = 0.f;
   // each warp walks RPW batch rows of channel c and reduces its weight-gradient / BN sums once at the end
   for (int r = 0; r < P.RPW; ++r) {
-  const int b = (blockIdx.y * P.RPW + r) * 8 + warp;
-  const bool ok = b < P.B;
+  const int b = (rg * P.RPW + r) * 8 + warp;
+  const bool ok = b < P.B && m0 < J.Lin;
   const float* xg = J.x + (long long)(ok ? b : 0) * J.xbs + (long long)c * J.Lin;
   __syncwarp();
   if (ok) {
-    _Pragma("unroll 4")
-    for (int p = lane; p < P.Wx; p += 32) {
-      const int pos = p - P.pad;
-      xrow[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xg[pos], J.tin, mean, rstd) : 0.f;
-    }
     const float* dg = J.du + (long long)b * J.dubs + (long long)c * J.Lo;
-    _Pragma("unroll 4")
-    for (int i = lane; i < P.Wd; i += 32) {
-      const int l = i - OFF;
-      drow[i] = (l >= 0 && l < J.Lo) ? dg[l] : 0.f;
+    float xv_[(WX + 31) / 32], dv_[(WD + 31) / 32];
+#pragma unroll
+    for (int q = 0; q < (WX + 31) / 32; ++q) {
+      const int pos = m0 - P.pad + lane + 32 * q;
+      xv_[q] = (pos >= 0 && pos < J.Lin) ? xg[pos] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < (WD + 31) / 32; ++q) {
+      const int l = l0 - OFF + lane + 32 * q;
+      dv_[q] = (l >= 0 && l < J.Lo) ? dg[l] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < (WX + 31) / 32; ++q) {
+      const int p = lane + 32 * q, pos = m0 - P.pad + p;
+      if (p < WX) xrow[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xv_[q], J.tin, mean, rstd) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < (WD + 31) / 32; ++q) {
+      const int i = lane + 32 * q;
+      if (i < WD) drow[i] = dv_[q];
     }
   }
   __syncwarp();
   if (ok) {
     float* orow = J.out + (long long)b * J.obs + (long long)c * J.Lin;
+    const int nm = m1 - m0, nl = l1 - l0;
     if (S == 1) {
-      // dr[m] = sum_t w[t] * du[m + pad - t*D];  window base (drow index) = m0 + pad - (K-1)*D + OFF = m0 + SH
+      // dr[m] = sum_t w[t] * du[m + pad - t*D];  window base (drow index) = (m - m0) + pad - (K-1)*D + OFF = ml + SH
       constexpr int SH = OFF - PADC;                      // 0..3
       constexpr int NW = (K - 1) * D + 4 + SH;
       constexpr int NW4 = (NW + 3) / 4;
-      for (int g4 = lane; g4 * 4 < J.Lin; g4 += 32) {
-        const int m0 = g4 * 4;
+      for (int g4 = lane; g4 * 4 < nm; g4 += 32) {
+        const int ml = g4 * 4, mg = m0 + ml;
         float dw_[NW4 * 4];
-        const float4* dp = reinterpret_cast<const float4*>(drow + m0);
+        const float4* dp = reinterpret_cast<const float4*>(drow + ml);
 #pragma unroll
         for (int q = 0; q < NW4; ++q) { const float4 v = dp[q]; dw_[4 * q] = v.x; dw_[4 * q + 1] = v.y; dw_[4 * q + 2] = v.z; dw_[4 * q + 3] = v.w; }
         float a[4] = {0.f, 0.f, 0.f, 0.f};
@@ -600,29 +630,29 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
         float xv[4], ov[4];
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
-          const bool in = m0 + n < J.Lin;
-          xv[n] = in ? xg[m0 + n] : 0.f;
-          ov[n] = (in && J.omode == O_RELU_ACC) ? orow[m0 + n] : 0.f;
+          const bool in = mg + n < J.Lin;
+          xv[n] = in ? xg[mg + n] : 0.f;
+          ov[n] = (in && J.omode == O_RELU_ACC) ? orow[mg + n] : 0.f;
         }
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
-          const int m = m0 + n;
+          const int m = mg + n;
           if (m < J.Lin) {
             if (J.omode == O_RELU_ACC) { if (xv[n] > 0.f) orow[m] = ov[n] + a[n]; }
             else { const float v = xv[n] > mean ? a[n] : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv[n], qq); }
           }
         }
       }
-      // dwd[c,t] += sum_l du[l] * T(x)[l + t*D - pad]   (xrow index = l + t*D)
+      // dwd[c,t] += sum_l du[l] * T(x)[l + t*D - pad]   (xrow index = (l - l0) + t*D)
       if (J.dwd) {
         constexpr int NR = (K - 1) * D + 4;
         constexpr int NR4 = (NR + 3) / 4;
-        for (int g4 = lane; g4 * 4 < J.Lo; g4 += 32) {
-          const int l0 = g4 * 4;
-          const float4 dv = *reinterpret_cast<const float4*>(drow + l0 + OFF);
+        for (int g4 = lane; g4 * 4 < nl; g4 += 32) {
+          const int ll = g4 * 4;
+          const float4 dv = *reinterpret_cast<const float4*>(drow + ll + OFF);
           const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
           float xw[NR4 * 4];
-          const float4* xp = reinterpret_cast<const float4*>(xrow + l0);
+          const float4* xp = reinterpret_cast<const float4*>(xrow + ll);
 #pragma unroll
           for (int q = 0; q < NR4; ++q) { const float4 v = xp[q]; xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w; }
 #pragma unroll
@@ -633,12 +663,13 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
       }
     } else {
       _Pragma("unroll 4")
-      for (int m = lane; m < J.Lin; m += 32) {
+      for (int ml = lane; ml < nm; ml += 32) {
+        const int m = m0 + ml;
         float a = 0.f;
 #pragma unroll
         for (int t = 0; t < K; ++t) {
           const int num = m + P.pad - t * D;
-          if (num >= 0 && num % S == 0) a = fmaf(w[t], drow[num / S + OFF], a);
+          if (num >= 0 && num % S == 0) a = fmaf(w[t], drow[num / S - l0 + OFF], a);
         }
         const float xv = xg[m];
         if (J.omode == O_RELU_ACC) { if (xv > 0.f) orow[m] += a; }
@@ -646,10 +677,10 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
       }
       if (J.dwd) {
         _Pragma("unroll 4")
-        for (int l = lane; l < J.Lo; l += 32) {
-          const float dv = drow[l + OFF];
+        for (int ll = lane; ll < nl; ll += 32) {
+          const float dv = drow[ll + OFF];
 #pragma unroll
-          for (int t = 0; t < K; ++t) gw[t] = fmaf(dv, xrow[l * S + t * D], gw[t]);
+          for (int t = 0; t < K; ++t) gw[t] = fmaf(dv, xrow[ll * S + t * D], gw[t]);
         }
       }
     }
@@ -678,58 +709,81 @@ struct PoolBwdJob {
   float* dx; long long dxbs;           // accumulated
   int Lin, Lo, skip_widx;              // skip_widx < 0: no identity skip on this edge
 };
-struct PoolBwdBatch { int n, B, C, S, Wx, Wd; const float* mixw; PoolBwdJob j[kMaxPool]; };
+struct PoolBwdBatch { int n, B, C, S, nseg; const float* mixw; PoolBwdJob j[kMaxPool]; };
 
+// CTA: channel c, 8 batch rows (one per warp), one segment of kPoolSeg input positions (a multiple of every stride)
+constexpr int kPoolSeg = 252, kPoolXO = 8, kPoolWX = kPoolSeg + 16, kPoolWD = kPoolSeg + 8;
 static __global__ void __launch_bounds__(kThreads) k_pool_bwd(const __grid_constant__ PoolBwdBatch P) {
   const PoolBwdJob& J = P.j[blockIdx.z];
   const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y * 8 + warp;
-  if (b >= P.B) return;
-  GNAS_DYN_SMEM(float, smem);
-  float* xrow = smem + warp * (P.Wx + 2 * P.Wd);
-  float* dm = xrow + P.Wx;     // dz of the max pool, index i <-> l = i - 4
-  float* da = dm + P.Wd;       // dz of the avg pool already divided by the window count
+  const int rg = blockIdx.y / P.nseg, seg = blockIdx.y - rg * P.nseg;
+  const int b = rg * 8 + warp;
   const int S = P.S;
+  const int m0 = seg * kPoolSeg, m1 = min(J.Lin, m0 + kPoolSeg);
+  if (b >= P.B || m0 >= J.Lin) return;
+  __shared__ float sm[8][kPoolWX + 2 * kPoolWD];
+  float* xrow = sm[warp];        // index p <-> pos = m0 - kPoolXO + p
+  float* dm = xrow + kPoolWX;    // dz of the max pool, index i <-> l = m0 / S - 4 + i
+  float* da = dm + kPoolWD;      // dz of the avg pool already divided by the window count
+  const int lb = m0 / S - 4;
+  const int nd = (m1 - m0 + 1) / S + 8;          // staged windows: l in [lb, lb + nd)
   const float* xg = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
   const float* gg = J.g + (long long)b * J.gbs + (long long)c * J.Lo;
-  _Pragma("unroll 4")
-  for (int p = lane; p < P.Wx; p += 32) {
-    const int pos = p - 2;
-    xrow[p] = (pos >= 0 && pos < J.Lin) ? xg[pos] : -INFINITY;
-  }
   const long long zo = ((long long)b * P.C + c) * J.Lo;
-  _Pragma("unroll 4")
-  for (int i = lane; i < P.Wd; i += 32) {
-    const int l = i - 4;
-    float vm = 0.f, va = 0.f;
-    if (l >= 0 && l < J.Lo) {
-      const float gv = gg[l];
-      if (J.zmax) vm = fmaf(J.coef_max[c], gv, fmaf(J.coef_max[P.C + c], J.zmax[zo + l], J.coef_max[2 * P.C + c]));
-      if (J.zavg) {
-        const int lo = max(l * S - 2, 0), hi = min(l * S + 2, J.Lin - 1);
-        va = fmaf(J.coef_avg[c], gv, fmaf(J.coef_avg[P.C + c], J.zavg[zo + l], J.coef_avg[2 * P.C + c])) / (float)(hi - lo + 1);
+  {
+    float xv[(kPoolWX + 31) / 32], gv[(kPoolWD + 31) / 32], zm[(kPoolWD + 31) / 32], za[(kPoolWD + 31) / 32];
+#pragma unroll
+    for (int q = 0; q < (kPoolWX + 31) / 32; ++q) {
+      const int pos = m0 - kPoolXO + lane + 32 * q;
+      xv[q] = (J.zmax && pos >= 0 && pos < J.Lin) ? xg[pos] : -INFINITY;
+    }
+#pragma unroll
+    for (int q = 0; q < (kPoolWD + 31) / 32; ++q) {
+      const int i = lane + 32 * q, l = lb + i;
+      const bool in = i < nd && l >= 0 && l < J.Lo;
+      gv[q] = in ? gg[l] : 0.f;
+      zm[q] = (in && J.zmax) ? J.zmax[zo + l] : 0.f;
+      za[q] = (in && J.zavg) ? J.zavg[zo + l] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < (kPoolWX + 31) / 32; ++q) {
+      const int p = lane + 32 * q;
+      if (p < kPoolWX) xrow[p] = xv[q];
+    }
+#pragma unroll
+    for (int q = 0; q < (kPoolWD + 31) / 32; ++q) {
+      const int i = lane + 32 * q, l = lb + i;
+      if (i < kPoolWD) {
+        float vm = 0.f, va = 0.f;
+        if (i < nd && l >= 0 && l < J.Lo) {
+          if (J.zmax) vm = fmaf(J.coef_max[c], gv[q], fmaf(J.coef_max[P.C + c], zm[q], J.coef_max[2 * P.C + c]));
+          if (J.zavg) {
+            const int lo = max(l * S - 2, 0), hi = min(l * S + 2, J.Lin - 1);
+            va = fmaf(J.coef_avg[c], gv[q], fmaf(J.coef_avg[P.C + c], za[q], J.coef_avg[2 * P.C + c])) / (float)(hi - lo + 1);
+          }
+        }
+        dm[i] = vm; da[i] = va;
       }
     }
-    dm[i] = vm; da[i] = va;
   }
   __syncwarp();
   const float wskip = J.skip_widx >= 0 ? P.mixw[J.skip_widx] : 0.f;
   float* drow = J.dx + (long long)b * J.dxbs + (long long)c * J.Lin;
   _Pragma("unroll 4")
-  for (int m = lane; m < J.Lin; m += 32) {
+  for (int m = m0 + lane; m < m1; m += 32) {
     float a = 0.f;
     // windows l with l*S-2 <= m <= l*S+2
     int l_lo = (m - 2 + S - 1) / S; if (m - 2 < 0) l_lo = 0;
     int l_hi = (m + 2) / S; if (l_hi > J.Lo - 1) l_hi = J.Lo - 1;
     for (int l = l_lo; l <= l_hi; ++l) {
-      a += da[l + 4];
+      a += da[l - lb];
       if (J.zmax) {
         // first maximal element of window l (torch max_pool1d backward routes there)
-        const float* wv = xrow + l * S;   // index 0 <-> pos l*S-2
+        const float* wv = xrow + (l * S - 2 - m0 + kPoolXO);   // index 0 <-> pos l*S-2
         int am = 0; float best = wv[0];
 #pragma unroll
         for (int t = 1; t < 5; ++t) if (wv[t] > best) { best = wv[t]; am = t; }
-        if (l * S - 2 + am == m) a += dm[l + 4];
+        if (l * S - 2 + am == m) a += dm[l - lb];
       }
     }
     if (J.skip_widx >= 0) {

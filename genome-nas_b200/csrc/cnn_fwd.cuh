@@ -206,36 +206,54 @@ struct DwJob {
   int Lin, Lout, tin;
 };
 constexpr int kMaxDw = 16;
-struct DwBatch { int n, B, C, pad, Wp; DwJob j[kMaxDw]; };
+struct DwBatch { int n, B, C, pad, nseg; DwJob j[kMaxDw]; };
 
-// u[b,c,l] = sum_t wd[c,t] * T(x)[b,c,l*S+t*D-pad];  CTA: batch row b, 8 channels (one per warp)
+// A row of outputs is cut into segments of SEGO positions (whole rows left the C = 8 cells with 1.5 CTAs per SM)
+template <int K, int D, int S>
+struct DwFwdGeom {
+  static constexpr int SEGO = S == 1 ? 256 : (S == 2 ? 128 : 84);              // multiples of 4
+  static constexpr int WP = (SEGO * S + (K - 1) * D + 3 * S + 8 + 3) / 4 * 4;   // staged inputs: index p <-> pos = l0*S - pad + p
+};
+
+// u[b,c,l] = sum_t wd[c,t] * T(x)[b,c,l*S+t*D-pad];  CTA: batch row b, 8 channels (one per warp), one output segment
 template <int K, int D, int S>
 __global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwBatch P) {
+  using G = DwFwdGeom<K, D, S>;
+  constexpr int SEGO = G::SEGO, WP = G::WP;
   const DwJob& J = P.j[blockIdx.z];
-  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y / P.nseg, seg = blockIdx.y - b * P.nseg;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 8 + warp;
+  const int l0 = seg * SEGO, l1 = min(J.Lout, l0 + SEGO);
   constexpr int NX = 3 * S + (K - 1) * D + 1;
   constexpr int NX4 = (NX + 3) / 4;
-  GNAS_DYN_SMEM(float, smem);
-  float* row = smem + warp * P.Wp;
-  if (c < P.C) {
+  __shared__ __align__(16) float rows[8][WP];
+  float* row = rows[warp];
+  if (c >= P.C || l0 >= J.Lout) return;
+  {
     const float* xr = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
     float mean = 0.f, rstd = 1.f;
     if (J.tin >= T_BN_RELU) { mean = J.in_stat[c]; rstd = J.in_stat[P.C + c]; }
-    _Pragma("unroll 4")
-    for (int p = lane; p < P.Wp; p += 32) {
-      const int pos = p - P.pad;
-      row[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xr[pos], J.tin, mean, rstd) : 0.f;
+    float xv[(WP + 31) / 32];
+#pragma unroll
+    for (int q = 0; q < (WP + 31) / 32; ++q) {
+      const int pos = l0 * S - P.pad + lane + 32 * q;
+      xv[q] = (pos >= 0 && pos < J.Lin) ? xr[pos] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < (WP + 31) / 32; ++q) {
+      const int p = lane + 32 * q, pos = l0 * S - P.pad + p;
+      if (p < WP) row[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xv[q], J.tin, mean, rstd) : 0.f;
     }
   }
   __syncwarp();
-  if (c >= P.C) return;
   float w[K];
 #pragma unroll
   for (int t = 0; t < K; ++t) w[t] = J.wd[c * K + t];
   float* ur = J.u + (long long)b * J.ubs + (long long)c * J.Lout;
   const bool vecok = (J.Lout % 4 == 0) && (J.ubs % 4 == 0);
-  for (int g = lane; g * 4 < J.Lout; g += 32) {
+  for (int g = lane; l0 + g * 4 < l1; g += 32) {
+    const int l = l0 + g * 4;
     float xw[NX4 * 4];
     const float4* xp = reinterpret_cast<const float4*>(row + g * 4 * S);
 #pragma unroll
@@ -245,9 +263,9 @@ __global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwB
     for (int t = 0; t < K; ++t)
 #pragma unroll
       for (int n = 0; n < 4; ++n) a[n] = fmaf(w[t], xw[n * S + t * D], a[n]);
-    if (vecok && g * 4 + 3 < J.Lout) *reinterpret_cast<float4*>(ur + g * 4) = make_float4(a[0], a[1], a[2], a[3]);
+    if (vecok && l + 3 < J.Lout) *reinterpret_cast<float4*>(ur + l) = make_float4(a[0], a[1], a[2], a[3]);
     else
-      for (int n = 0; n < 4; ++n) if (g * 4 + n < J.Lout) ur[g * 4 + n] = a[n];
+      for (int n = 0; n < 4; ++n) if (l + n < J.Lout) ur[l + n] = a[n];
   }
 }
 
@@ -259,21 +277,24 @@ struct PoolJob {
   int Lin, Lout;
 };
 constexpr int kMaxPool = 8;
-struct PoolBatch { int n, B, C, S; PoolJob j[kMaxPool]; };
+struct PoolBatch { int n, B, C, S, nseg; PoolJob j[kMaxPool]; };
+constexpr int kPoolFwdSeg = 256;      // outputs per CTA row segment
 
 // MaxPool1d(5,pad 2, -inf padding) and AvgPool1d(5,pad 2,count_include_pad=False) in one pass over x.
 // CTA: channel c (blockIdx.x), 8 batch rows (one per warp).
 static __global__ void __launch_bounds__(kThreads) k_pool_fwd(const __grid_constant__ PoolBatch P) {
   const PoolJob& J = P.j[blockIdx.z];
   const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y * 8 + warp;
+  const int rg = blockIdx.y / P.nseg, seg = blockIdx.y - rg * P.nseg;
+  const int b = rg * 8 + warp;
+  const int l0 = seg * kPoolFwdSeg, l1 = min(J.Lout, l0 + kPoolFwdSeg);
   __shared__ float red[4][8];
   float sm = 0.f, qm = 0.f, sa = 0.f, qa = 0.f;
   if (b < P.B) {
     const float* xr = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
     const long long o = ((long long)b * P.C + c) * J.Lout;
-    _Pragma("unroll 4")
-    for (int l = lane; l < J.Lout; l += 32) {
+    _Pragma("unroll 8")
+    for (int l = l0 + lane; l < l1; l += 32) {
       const int s0 = l * P.S - 2;
       float mx = -INFINITY, sum = 0.f;
       int cnt = 0;

@@ -78,21 +78,11 @@ static int launch_dense_fwd(int KW, int S, DenseBatch& b, cudaStream_t st) {
 // ------------------------------------------------------------------ depthwise forward
 template <int K, int D, int S>
 static void launch_dw_fwd_t(DwBatch& b, cudaStream_t st) {
-  constexpr int NX = 3 * S + (K - 1) * D + 1;
-  constexpr int NX4 = (NX + 3) / 4;
-  int wp = 0;
-  for (int i = 0; i < b.n; ++i) {
-    const int g4 = cdiv(b.j[i].Lout, 4);
-    int need = (g4 - 1) * 4 * S + NX4 * 4;
-    const int need2 = b.pad + b.j[i].Lin;
-    need = need > need2 ? need : need2;
-    wp = need > wp ? need : wp;
-  }
-  b.Wp = round_up(wp, 4) + 4;
-  const size_t smem = sizeof(float) * 8 * (size_t)b.Wp;
-  GNAS_PREP_SMEM((k_dw_fwd<K, D, S>), smem);
-  dim3 grid(cdiv(b.C, 8), b.B, b.n);
-  GNAS_LAUNCH((k_dw_fwd<K, D, S>), grid, dim3(kThreads), smem, st, b);
+  int lout = 1;
+  for (int i = 0; i < b.n; ++i) lout = b.j[i].Lout > lout ? b.j[i].Lout : lout;
+  b.nseg = cdiv(lout, DwFwdGeom<K, D, S>::SEGO);
+  dim3 grid(cdiv(b.C, 8), b.B * b.nseg, b.n);
+  GNAS_LAUNCH((k_dw_fwd<K, D, S>), grid, dim3(kThreads), 0, st, b);
 }
 static int launch_dw_fwd(int K, int D, int S, DwBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
@@ -247,34 +237,17 @@ static int launch_conv_wgrad(int KW, int S, int pad, WgBatch& b, cudaStream_t st
 // ------------------------------------------------------------------ depthwise backward
 template <int K, int D, int S>
 static void launch_dw_bwd_t(DwBwdBatch& b, cudaStream_t st) {
-  constexpr int PADC = (K - 1) * D / 2;
-  constexpr int OFF = S == 1 ? (PADC + 3) / 4 * 4 : K;
-  int wx = 0, wd = 0;
-  for (int i = 0; i < b.n; ++i) {
-    const int Lin = b.j[i].Lin, Lo = b.j[i].Lo;
-    // x row: index p <-> pos = p - pad; windows of the vector path read up to round4(Lo) + (K-1)*D + 8
-    int a = Lin + 2 * b.pad;
-    const int a2 = (Lo - 1) * S + (K - 1) * D + 1;
-    const int a3 = round_up(Lo, 4) + (K - 1) * D + 8;
-    a = a > a2 ? a : a2;
-    a = a > a3 ? a : a3;
-    wx = a > wx ? a : wx;
-    // du row: index i <-> l = i - OFF; vector path reads up to round4(Lin) + (K-1)*D + 12
-    int d = (Lin + b.pad) / S + OFF + 2;
-    const int d2 = Lo + OFF + 8;
-    const int d3 = round_up(Lin, 4) + (K - 1) * D + 12;
-    d = d > d2 ? d : d2;
-    d = d > d3 ? d : d3;
-    wd = d > wd ? d : wd;
-  }
-  b.Wx = round_up(wx, 4); b.Wd = round_up(wd, 4);
-  const size_t smem = sizeof(float) * 8 * (size_t)(b.Wx + b.Wd);
+  using G = DwBwdGeom<K, D, S>;
+  int lin = 1;
+  for (int i = 0; i < b.n; ++i) lin = b.j[i].Lin > lin ? b.j[i].Lin : lin;
+  b.nseg = cdiv(lin, G::SEG);
+  const size_t smem = sizeof(float) * 8 * (size_t)(G::WX + G::WD);
   GNAS_PREP_SMEM((k_dw_bwd<K, D, S>), smem);
-  // rows per warp: keep >= ~2 CTAs per SM, reduce the per-row reduction/atomic overhead when rows are short
-  int rpw = (b.C * cdiv(b.B, 8) * b.n) / (16 * 148);      // only when the grid is far larger than the machine
+  // rows per warp: reduce the per-row reduction/atomic overhead only when the grid is far larger than the machine
+  int rpw = (b.C * cdiv(b.B, 8) * b.n * b.nseg) / (16 * 148);
   rpw = rpw < 1 ? 1 : (rpw > 2 ? 2 : rpw);
   b.RPW = rpw;
-  dim3 grid(b.C, cdiv(b.B, 8 * rpw), b.n);
+  dim3 grid(b.C, cdiv(b.B, 8 * rpw) * b.nseg, b.n);
   GNAS_LAUNCH((k_dw_bwd<K, D, S>), grid, dim3(kThreads), smem, st, b);
 }
 static int launch_dw_bwd(int K, int D, int S, DwBwdBatch& b, cudaStream_t st) {
@@ -294,26 +267,21 @@ static int launch_dw_bwd(int K, int D, int S, DwBwdBatch& b, cudaStream_t st) {
 // ------------------------------------------------------------------ pools
 static int launch_pool_fwd(PoolBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
-  dim3 grid(b.C, cdiv(b.B, 8), b.n);
+  int lout = 1;
+  for (int i = 0; i < b.n; ++i) lout = b.j[i].Lout > lout ? b.j[i].Lout : lout;
+  b.nseg = cdiv(lout, kPoolFwdSeg);
+  dim3 grid(b.C, cdiv(b.B, 8) * b.nseg, b.n);
   GNAS_LAUNCH(k_pool_fwd, grid, dim3(kThreads), 0, st, b);
   b.n = 0;
   return 0;
 }
 static int launch_pool_bwd(PoolBwdBatch& b, cudaStream_t st) {
   if (b.n == 0) return 0;
-  int wx = 0, wd = 0;
-  for (int i = 0; i < b.n; ++i) {
-    int a = b.j[i].Lin + 4;
-    const int a2 = (b.j[i].Lo - 1) * b.S + 5;
-    a = a > a2 ? a : a2;
-    wx = a > wx ? a : wx;
-    wd = b.j[i].Lo + 8 > wd ? b.j[i].Lo + 8 : wd;
-  }
-  b.Wx = wx; b.Wd = wd;
-  const size_t smem = sizeof(float) * 8 * (size_t)(b.Wx + 2 * b.Wd);
-  GNAS_PREP_SMEM(k_pool_bwd, smem);
-  dim3 grid(b.C, cdiv(b.B, 8), b.n);
-  GNAS_LAUNCH(k_pool_bwd, grid, dim3(kThreads), smem, st, b);
+  int lin = 1;
+  for (int i = 0; i < b.n; ++i) lin = b.j[i].Lin > lin ? b.j[i].Lin : lin;
+  b.nseg = cdiv(lin, kPoolSeg);
+  dim3 grid(b.C, cdiv(b.B, 8) * b.nseg, b.n);
+  GNAS_LAUNCH(k_pool_bwd, grid, dim3(kThreads), 0, st, b);
   b.n = 0;
   return 0;
 }

@@ -602,7 +602,7 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem(const __grid_c
           }
           dc = dr * g * (1.f - g) * (F - q * sj);
           dh = dr * g * Fp;
-          dsj[m] += dr * q * (1.f - g);
+          atomicAdd(&dsj[m], dr * q * (1.f - g));     // the products of earlier nodes may still be landing in ds_j
         }
         cp[m] = dc; hp[m] = dh;
       }
@@ -673,13 +673,14 @@ static __global__ void __launch_bounds__(256) k_transpose(const float* src, floa
 // CTA tile: 64 rows n x BP columns m, K range = K / ksplit, cp.async double-buffered 32-row K chunks.
 struct RhnGemm {
   int Nrows, K, BP, nz, ksplit, Hsplit;   // rows >= Hsplit go to out2/mask2 (stage 0: dx rows | dh rows)
+  int z0;                                 // first problem of this launch: z = z0 + blockIdx.z
   const float* WT; int ldw;               // WT[k][n], row pitch ldw (= Nrows)
   const float* D[8]; float* out[8];
   const float* mask; float* out2; const float* mask2;
 };
 constexpr int kGemmKC = 32;
 static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_gemm(const __grid_constant__ RhnGemm P) {
-  const int z = blockIdx.z;
+  const int z = P.z0 + blockIdx.z;
   const int n0 = blockIdx.x * 64;
   const int kper = P.K / P.ksplit;
   const int kbeg = blockIdx.y * kper;
@@ -949,6 +950,38 @@ extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const floa
   return check_launch("gnas_rhn_forward");
 }
 
+// A second stream per device for the off-critical-path products of the backward recurrence (fork / join by events,
+// which a CUDA-graph capture of the caller's stream records as plain dependencies).  GNAS_RHN_SIDE=0 disables it.
+#ifdef GNAS_EMUL      // the emulator has one in-order queue: the side stream is never created, these are never called
+typedef void* cudaEvent_t;
+static inline int cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline int cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return 0; }
+#endif
+struct SideStream { cudaStream_t st; cudaEvent_t fork; cudaEvent_t join[2]; };
+static SideStream side_stream() {
+  SideStream none; none.st = nullptr; none.fork = nullptr; none.join[0] = none.join[1] = nullptr;
+#ifdef GNAS_EMUL
+  return none;
+#else
+  static SideStream table[kMaxDevices];
+  static bool made[kMaxDevices] = {false};
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("GNAS_RHN_SIDE"); enabled = e ? atoi(e) : 1; }
+  int dev = 0;
+  if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return none;
+  if (!made[dev]) {
+    SideStream s;
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return none;
+    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join[1], cudaEventDisableTiming);
+    table[dev] = s;
+    made[dev] = true;
+  }
+  return table[dev];
+#endif
+}
+
 extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const float* h0, const float* W0,
                                  const float* Ws, const float* probs, const float* x_mask, const float* h_mask,
                                  const float* dout, float* ws, float* scratch, float* dx, float* dh0,
@@ -992,6 +1025,7 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
     if (need_prepare(prepared, (int)gsm)) cudaFuncSetAttribute(k_rhn_bwd_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm); }
 #endif
   if (nch_g > 4 || nch_g < 1) { set_error("rhn_backward: unsupported hidden size for the GEMM split"); return GNAS_ERR_UNSUPPORTED; }
+  const SideStream side = side_stream();
   for (int t = T - 1; t >= 0; --t) {
     float* dh_cur = dhbuf[(T - 1 - t) & 1];
     float* dh_next = dhbuf[(T - t) & 1];
@@ -1008,7 +1042,24 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
         g.out[j] = scratch + p.dsT + (size_t)j * HB;
       }
       g.mask = ws + p.hmT; g.out2 = nullptr; g.mask2 = nullptr;
-      GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((H + 63) / 64, g.ksplit, i + 1), dim3(kThreads), gsm, st, g);
+      // Only the product of edge (i, i) feeds the next stage (ds_i is complete once it has landed); the products
+      // of the edges (i, j < i) are needed at stage j at the earliest, so they run on a side stream next to the
+      // following elementwise kernel and critical product instead of in front of them.
+      if (side.st) {
+        g.z0 = i; g.nz = 1;
+        if (i > 0) { cudaEventRecord(side.fork, st); cudaStreamWaitEvent(side.st, side.fork, 0); }
+        GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((H + 63) / 64, g.ksplit, 1), dim3(kThreads), gsm, st, g);
+        // stage i - 1 reads ds_i: every side product into it was issued at stage i + 1 or before
+        if (i < 7) cudaStreamWaitEvent(st, side.join[(i + 1) & 1], 0);
+        if (i > 0) {
+          g.z0 = 0; g.nz = i;
+          GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((H + 63) / 64, g.ksplit, i), dim3(kThreads), gsm, side.st, g);
+          cudaEventRecord(side.join[i & 1], side.st);
+        }
+      } else {
+        g.z0 = 0;
+        GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((H + 63) / 64, g.ksplit, i + 1), dim3(kThreads), gsm, st, g);
+      }
     }
     GNAS_LAUNCH(k_rhn_bwd_elem0, dim3(eb), dim3(kThreads), 0, st, bp);
     RhnGemm g;
@@ -1016,7 +1067,7 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
     g.WT = scratch + p.W0T; g.ldw = 2 * H;
     g.D[0] = ws + p.C0T + ((size_t)t * 2) * HB;
     g.out[0] = scratch + p.dxT + (size_t)t * HB; g.mask = ws + p.xkT;
-    g.out2 = dh_next; g.mask2 = ws + p.hmT;
+    g.out2 = dh_next; g.mask2 = ws + p.hmT; g.z0 = 0;
     GNAS_LAUNCH(k_rhn_bwd_gemm, dim3((2 * H + 63) / 64, g.ksplit, 1), dim3(kThreads), gsm, st, g);
   }
   // outputs: dx [T][B][H], dh0 [B][H], dprobs

@@ -22,6 +22,7 @@ from . import _lib
 from .cnn import _FusedBase, _FusedCellFunction, _fill_edge
 from .model import _StemFunction
 from .flat import region_of
+from .head import criterion_loss, head_forward
 from .operations import OPS, PRIMITIVES_cnn, PRIMITIVES_rnn, FactorizedReduce, ReLUConvBN, rnn_steps
 from .rnn import INITRANGE, _RhnFunction, mask2d  # noqa: F401  (mask2d: same CPU-generator draw order)
 from . import rnn as _rnn
@@ -204,6 +205,8 @@ class DARTSCellSearch(_rnn.DARTSCellSearch):
 
 
 class RNNModel(nn.Module):
+    _head_wgrad = True
+
     """model.py:248-471 (search=True)."""
 
     def __init__(self, seq_len, dropouth=0.5, dropoutx=0.5, C=8, num_classes=4, layers=3, steps=4, multiplier=4,
@@ -258,10 +261,7 @@ class RNNModel(nn.Module):
         hidden = new_hidden
         output = raw_output
         outputs.append(output)
-        x = torch.flatten(output.permute(1, 0, 2), start_dim=1)
-        x = self.dropout_lin(x)
-        x = self.relu(self.decoder(x))
-        logit = self.final(self.classifier(x))
+        logit = head_forward(self, output)
         if return_h:
             return logit, hidden, raw_outputs, outputs
         return logit, hidden
@@ -284,4 +284,4 @@ class RNNModelSearch(RNNModel):
     def _loss(self, hidden, input, target, criterion, mask=None):
         log_prob, hidden_next = self(input, hidden, mask if mask is not None else
                                      [self.mask_normal, self.mask_reduce, self.mask_rnn], return_h=False)
-        return criterion(log_prob, target), hidden_next
+        return criterion_loss(criterion, log_prob, target), hidden_next

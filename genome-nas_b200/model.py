@@ -20,6 +20,7 @@ import torch.nn.functional as F
 from . import _lib
 from .cnn import CNN_Cell_search
 from .flat import region_of
+from .head import criterion_loss, head_forward
 from .operations import CONCAT, PRIMITIVES_cnn, PRIMITIVES_rnn, rnn_steps
 from .rnn import INITRANGE, DARTSCellSearch
 from collections import namedtuple
@@ -132,6 +133,8 @@ class RNNModel(nn.Module):
         self.init_weights()
         self.ninp = self.nhid = self.nhidlast = out_channels
 
+    _head_wgrad = True
+
     def init_weights(self):
         self.decoder.bias.data.fill_(0)
         self.decoder.weight.data.uniform_(-INITRANGE, INITRANGE)
@@ -145,6 +148,7 @@ class RNNModel(nn.Module):
         """Disable the weight-gradient kernels for passes whose weight gradients are discarded
         (the first-order alpha step: architect.py:69-72 + train_and_validate.py:112)."""
         self.stem._wgrad_enabled = enabled
+        self._head_wgrad = enabled
         for cell in self.cells:
             cell._wgrad_enabled = enabled
         for rnn in self.rnns:
@@ -177,10 +181,7 @@ class RNNModel(nn.Module):
         hidden = new_hidden
         output = raw_output
         outputs.append(output)
-        x = torch.flatten(output.permute(1, 0, 2), start_dim=1)
-        x = self.dropout_lin(x)
-        x = self.relu(self.decoder(x))
-        logit = self.final(self.classifier(x))
+        logit = head_forward(self, output)          # permute/flatten, dropout_lin, decoder, relu, classifier, final
         if return_h:
             return logit, hidden, raw_outputs, outputs
         return logit, hidden
@@ -209,7 +210,7 @@ class RNNModelSearch(RNNModel):
 
     def _loss(self, hidden, input, target, criterion):
         log_prob, hidden_next = self(input, hidden, return_h=False)
-        return criterion(log_prob, target), hidden_next
+        return criterion_loss(criterion, log_prob, target), hidden_next
 
     def arch_parameters(self):
         return self._arch_parameters

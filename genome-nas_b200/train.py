@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from .head import bce_loss, criterion_loss, tar_loss
 
 
 class Hyper:
@@ -33,9 +34,6 @@ class Hyper:
     arch_clip = None
 
 
-def tar_loss(rnn_h, beta):
-    """Temporal activation regularisation, train_and_validate.py:140."""
-    return beta * (rnn_h[1:] - rnn_h[:-1]).pow(2).mean()
 
 
 class SearchStep:
@@ -74,7 +72,7 @@ class SearchStep:
         model.set_weight_grads(False)
         try:
             logits, _ = model(x_valid, model.init_hidden(x_valid.size(0)))
-            loss = F.binary_cross_entropy(logits, y_valid)
+            loss = bce_loss(logits, y_valid)
             loss.backward()
         finally:
             model.set_weight_grads(True)
@@ -115,7 +113,7 @@ class SearchStep:
         if zero:
             g.zero_()
         logits, hidden, rnn_hs, _ = model(x_train, model.init_hidden(x_train.size(0)), return_h=True)
-        raw = F.binary_cross_entropy(logits, y_train)
+        raw = bce_loss(logits, y_train)
         loss = raw + tar_loss(rnn_hs[-1], self.h.beta)
         loss.backward()
         return loss.detach(), raw.detach(), logits.detach()
@@ -267,7 +265,7 @@ def train(train_queue, valid_queue, model, rhn, conv, criterion, optimizer, opti
             if pdarts:
                 optimizer_a.zero_grad()
                 logits, hidden, _, _ = model(inp_s, hidden, return_h=True)
-                criterion(logits, tgt_s).backward()
+                criterion_loss(criterion, logits, tgt_s).backward()
                 torch.nn.utils.clip_grad_norm_(model.arch_parameters(), clip_params[2])
                 optimizer_a.step()
             else:
@@ -275,7 +273,7 @@ def train(train_queue, valid_queue, model, rhn, conv, criterion, optimizer, opti
         optimizer.zero_grad()
         hidden = model.init_hidden(bsz)
         logits, hidden, rnn_hs, _ = model(inp, hidden, return_h=True)
-        raw_loss = criterion(logits, target)
+        raw_loss = criterion_loss(criterion, logits, target)
         loss = raw_loss + sum(tar_loss(h, beta) for h in rnn_hs[-1:])
         loss.backward()
         if one_clip:
@@ -285,6 +283,29 @@ def train(train_queue, valid_queue, model, rhn, conv, criterion, optimizer, opti
             torch.nn.utils.clip_grad_norm_(rhn, clip_params[1])
         optimizer.step()
         total += float(loss.detach()) * bsz
+        count += bsz
+        labels.append(target.detach().cpu().numpy())
+        out = torch.softmax(logits, -1) if task == "next_character_prediction" else logits
+        predictions.append(out.detach().cpu().numpy())
+    return labels, predictions, np.float32(total / max(count, 1))
+
+
+def infer(valid_queue, model, criterion, batch_size, num_steps, report_freq, task=None):
+    """Drop-in for generalNAS_tools/train_and_validate.py:182-232: eval-mode (running-statistics BatchNorm, no
+    dropout masks) forward over the validation queue; returns (labels, predictions, sample-weighted mean loss)."""
+    import numpy as np
+    dev = next(model.parameters()).device
+    model.eval()
+    labels, predictions, total, count = [], [], 0.0, 0
+    for step, (inp, target) in enumerate(valid_queue):
+        if step > num_steps:
+            break
+        inp, target = inp.to(dev).float(), target.to(dev)
+        bsz = inp.size(0)
+        with torch.no_grad():
+            logits, _ = model(inp, model.init_hidden(bsz))
+            loss = criterion_loss(criterion, logits, target)
+        total += float(loss) * bsz
         count += bsz
         labels.append(target.detach().cpu().numpy())
         out = torch.softmax(logits, -1) if task == "next_character_prediction" else logits

@@ -124,6 +124,30 @@ int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const float* h0, con
                       const float* dout, float* ws, float* scratch, float* dx, float* dh0,
                       float* dW0, float* dWs, float* dprobs, int need_wgrad, void* stream);
 
+/* ---- classification head: permute(1,0,2) + flatten + Dropout + Linear(T*H, D1) + ReLU + Linear(D1, NC)
+ * (+ Sigmoid when sigmoid = 1): darts_tools/model_discCNN.py:547-566.
+ * hs [T][B][H] (the RHN output); drop_mask [B][T*H] = keep / (1 - p) or null; Wd [D1][T*H], bd [D1],
+ * Wc [NC][D1], bc [NC] (bias pointers may be null); out [B][NC].  ws (gnas_head_workspace, 16-byte aligned) is kept
+ * until backward.  Backward overwrites dhs [T][B][H] and, when need_wgrad = 1, ACCUMULATES dWd / dbd / dWc / dbc. */
+int gnas_head_workspace(int T, int B, int H, int D1, int NC, int64_t* fwd_floats, int64_t* bwd_floats);
+int gnas_head_forward(int T, int B, int H, int D1, int NC, int sigmoid, const float* hs,
+                      const float* drop_mask, const float* Wd, const float* bd, const float* Wc,
+                      const float* bc, float* out, float* ws, void* stream);
+int gnas_head_backward(int T, int B, int H, int D1, int NC, int sigmoid, const float* drop_mask,
+                       const float* Wd, const float* Wc, const float* out, const float* dout,
+                       const float* ws, float* scratch, float* dhs, float* dWd, float* dbd,
+                       float* dWc, float* dbc, int need_wgrad, void* stream);
+
+/* ---- loss terms of the search step: generalNAS_tools/train_and_validate.py:136-140.
+ * gnas_bce_*: torch.nn.BCELoss(reduction='mean') over n probabilities (logs clamped at -100; backward divides by
+ * max(p (1 - p), 1e-12)); gnas_tar_*: mean((h[1:] - h[:-1])^2) over h [T][BH] (the caller scales by beta).
+ * loss / gout are DEVICE scalars; ws holds gnas_loss_workspace floats; sums run in double in a fixed order. */
+int gnas_loss_workspace(int64_t* floats);
+int gnas_bce_forward(const float* p, const float* y, int64_t n, float* loss, float* ws, void* stream);
+int gnas_bce_backward(const float* p, const float* y, const float* gout, int64_t n, float* dp, void* stream);
+int gnas_tar_forward(const float* h, int T, int64_t BH, float* loss, float* ws, void* stream);
+int gnas_tar_backward(const float* h, const float* gout, int T, int64_t BH, float* dh, void* stream);
+
 /* ---- optimiser steps on flat buffers.
  * gnas_grad_sumsq: out[0] += sum g^2 (double) -- global-norm clip, train_and_validate.py:146-147.
  * gnas_sgd_step:   torch.optim.SGD semantics (weight decay, momentum, first-step buffer copy),

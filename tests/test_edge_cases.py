@@ -37,6 +37,10 @@ def _oracle_mixed(m, x, w, switch, stride, P, skip_mask=None, p=0.0):
     (2, 64, 125, 1, [False] * 8 + [True]),                       # one partial tile (cell 4 geometry)
     (3, 128, 42, 1, [False] * 8 + [True]),                       # cell 5 geometry
     (2, 64, 125, 2, [False] * 8 + [True]),                       # strided first conv (SIMT) + stride-1 second conv
+    # rows longer than one depthwise / pool segment (256 positions at stride 1, 252 at stride 2 / 3):
+    (2, 8, 1000, 1, [True] * 9),                                 # cell 0 geometry: 4 segments
+    (2, 8, 530, 2, [True] * 9),                                  # 3 segments, ragged last one, 530 -> 265
+    (9, 8, 520, 3, [False, True, True, True, True, True, True, True, False]),    # 3 segments at stride 3, 520 -> 174
 ])
 def test_mixedop_shapes(backend, B, C, L, stride, switch):
     torch.manual_seed(B * 100 + L)

@@ -323,3 +323,21 @@ def test_unrolled_architect_matches_reference(backend):
     # the weights themselves are untouched by the architecture step (perturbed by +R, -2R, +R)
     P = O.synthetic_params(g["shapes"], g["seed_params"])
     assert relerr(dict(m.named_parameters())["stem.0.weight"], P["stem.0.weight"]) < 1e-6
+
+
+def test_infer_matches_oracle_eval_mode(backend):
+    """infer() (train_and_validate.py:182-232): eval-mode forward (running statistics, no masks) and the
+    sample-weighted mean BCE over the queue, against the CPU oracle in fp64."""
+    g = load("tiny")
+    cfg = g["cfg"]
+    m, P = build(g, backend)
+    batches = [O.synthetic_batch(g["B"], cfg.seq_len, cfg.num_classes, s) for s in (3, 4)]
+    labels, preds, avg = G.infer(batches, m, torch.nn.BCELoss(), g["B"], 10, 1000, cfg.task)
+    assert not m.training and len(preds) == 2
+    Q = {k: (v.double() if v.is_floating_point() else v) for k, v in P.items()}
+    tot = 0.0
+    for (x, y), p in zip(batches, preds):
+        lo, _ = O.supernet_forward(Q, cfg, x.double(), None, None, False, O.Recorder())
+        assert relerr(torch.from_numpy(p), lo) < 1e-5
+        tot += float(F.binary_cross_entropy(lo, y.double()))
+    assert abs(float(avg) - tot / 2) < 1e-5 * (tot / 2)
