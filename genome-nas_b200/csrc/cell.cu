@@ -748,9 +748,9 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     }
     c.rc |= pw_dx(xb);
     c.rc |= pw_wg(gb);
-    // -- depthwise: sep stage 2 (-> dyh1 + inner BN sums), dil (-> dX)
-    for (int v = 0; v < 4; ++v) {
-      const bool sep = v < 2;
+    // -- depthwise: sep stage 2 (-> dyh1 + inner BN sums); the dil depthwise convs (-> dX) join the fused edge kernel below
+    for (int v = 0; v < 2; ++v) {
+      const bool sep = true;
       DwBwdBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = dwP[v];
       for (int i = 0; i < n2; ++i) {
         const int e = es[i];
@@ -822,18 +822,25 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     }
     c.rc |= pw_dx(xb);
     c.rc |= pw_wg(gb);
-    for (int v = 0; v < 2; ++v) {
-      DwBwdBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = dwP[v];
+    // fused: every depthwise candidate that writes dX of the edge (sep stage 1: du1, dil: du) in one pass over x
+    {
+      EdgeBwdBatch eb; eb.n = 0; eb.B = B; eb.C = C;
       for (int i = 0; i < n2; ++i) {
         const int e = es[i];
-        const OpPlan& O = c.P.e[e].op[dwk[v]];
-        if (!O.on) continue;
-        DwBwdJob& j = wb.j[wb.n++];
-        j.du = tmp(i, tmp0[v] + 2); j.dubs = obs; c.src(e, j.x, j.xbs); j.in_stat = nullptr; j.wd = c.W(e, dwk[v], 0);
-        j.out = dsrc[is[i]]; j.obs = dsrc_bs[is[i]]; j.bacc = nullptr;
-        j.dwd = need_wgrad ? c.dW(e, dwk[v], 0) : nullptr; j.Lin = Lin; j.Lo = Lo; j.tin = T_RELU; j.omode = O_RELU_ACC;
+        bool any = false;
+        for (int v = 0; v < 4; ++v) any = any || c.P.e[e].op[dwk[v]].on;
+        if (!any) continue;
+        EdgeBwdJob& j = eb.j[eb.n++];
+        for (int v = 0; v < 4; ++v) {
+          const bool on = c.P.e[e].op[dwk[v]].on;
+          j.du[v] = on ? tmp(i, tmp0[v] + (v < 2 ? 2 : 0)) : nullptr;
+          j.wd[v] = on ? c.W(e, dwk[v], 0) : nullptr;
+          j.dwd[v] = (on && need_wgrad) ? c.dW(e, dwk[v], 0) : nullptr;
+        }
+        j.dubs = obs; c.src(e, j.x, j.xbs); j.out = dsrc[is[i]]; j.obs = dsrc_bs[is[i]]; j.Lin = Lin; j.Lo = Lo;
+        if (eb.n == kMaxEdgeJobs) c.rc |= launch_edge_bwd(S, eb, c.st);
       }
-      c.rc |= launch_dw_bwd(dwK[v], 1, S, wb, c.st);
+      c.rc |= launch_edge_bwd(S, eb, c.st);
     }
     // -- conv_15 first conv: dX, dW1
     xb.pad = 7;

@@ -553,7 +553,7 @@ struct DwBwdGeom {
 // of strided edges): every lane produces 4 consecutive positions from register windows (128-bit shared loads, static
 // tap indices).  The staging loops have compile-time bounds: all global loads of a tile are in flight at once.
 template <int K, int D, int S>
-__global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwBwdBatch P) {
+__global__ void __launch_bounds__(kThreads, 4) k_dw_bwd(const __grid_constant__ DwBwdBatch P) {
   using G = DwBwdGeom<K, D, S>;
   constexpr int PADC = G::PADC, OFF = G::OFF, SEG = G::SEG, WX = G::WX, WD = G::WD;
   static_assert(SEG % S == 0 && SEG % 4 == 0, "segment must be a multiple of the stride and of 4");
@@ -565,9 +565,9 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
   const int l0 = m0 / S;                                  // du positions l with l*S in [m0, m1)
   const int l1 = m1 > m0 ? min(J.Lo, (m1 - 1) / S + 1) : l0;
   GNAS_DYN_SMEM(float, smem);
-  float* xrow = smem + warp * (WX + WD);       // T(x) with zero halo
+  float* xrow = smem + warp * (WX + WD + SEG);   // T(x) with zero halo
   float* drow = xrow + WX;                     // du with zero halo
-  __shared__ float red[8][K + 2];
+  float* arow = drow + WD;                     // dx of the segment before masking (stride 1)
   float mean = 0.f, rstd = 1.f;
   if (J.tin >= T_BN_RELU) { mean = J.in_stat[c]; rstd = J.in_stat[P.C + c]; }
   float w[K];
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
       constexpr int NW = (K - 1) * D + 4 + SH;
       constexpr int NW4 = (NW + 3) / 4;
       for (int g4 = lane; g4 * 4 < nm; g4 += 32) {
-        const int ml = g4 * 4, mg = m0 + ml;
+        const int ml = g4 * 4;
         float dw_[NW4 * 4];
         const float4* dp = reinterpret_cast<const float4*>(drow + ml);
 #pragma unroll
@@ -627,21 +627,16 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
         for (int t = 0; t < K; ++t)
 #pragma unroll
           for (int n = 0; n < 4; ++n) a[n] = fmaf(w[t], dw_[SH + n + (K - 1 - t) * D], a[n]);
-        float xv[4], ov[4];
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const bool in = mg + n < J.Lin;
-          xv[n] = in ? xg[mg + n] : 0.f;
-          ov[n] = (in && J.omode == O_RELU_ACC) ? orow[mg + n] : 0.f;
-        }
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const int m = mg + n;
-          if (m < J.Lin) {
-            if (J.omode == O_RELU_ACC) { if (xv[n] > 0.f) orow[m] = ov[n] + a[n]; }
-            else { const float v = xv[n] > mean ? a[n] : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv[n], qq); }
-          }
-        }
+        *reinterpret_cast<float4*>(arow + ml) = make_float4(a[0], a[1], a[2], a[3]);
+      }
+      __syncwarp();
+      // the global read-modify-write walks the segment lane-interleaved: every access is one full 128-byte line per
+      // warp whatever the alignment of the row (4 consecutive positions per lane cost 4 partial-sector requests each)
+      _Pragma("unroll 4")
+      for (int ml = lane; ml < nm; ml += 32) {
+        const int m = m0 + ml;
+        if (J.omode == O_RELU_ACC) { if (xrow[ml + P.pad] > 0.f) orow[m] += arow[ml]; }
+        else { const float xv = xg[m]; const float v = xv > mean ? arow[ml] : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv, qq); }
       }
       // dwd[c,t] += sum_l du[l] * T(x)[l + t*D - pad]   (xrow index = (l - l0) + t*D)
       if (J.dwd) {
@@ -686,16 +681,209 @@ __global__ void __launch_bounds__(kThreads) k_dw_bwd(const __grid_constant__ DwB
     }
   }
   }   // rows
+  // CTA reduction of the K weight-gradient taps (weight pass only) and the two BN sums (stage-2 depthwise only)
+  // through shared memory: 17 shuffle reductions per warp cost more instructions than the tile itself
+  __syncthreads();                              // the row buffers are dead: reuse them as [K + 2][256]
+  float* part = smem;
+  const bool want_w = J.dwd != nullptr, want_s = J.omode == O_BNRELU_STORE;
+  if (want_w) {
 #pragma unroll
-  for (int t = 0; t < K; ++t) { gw[t] = warp_sum(gw[t]); if (lane == 0) red[warp][t] = gw[t]; }
-  s = warp_sum(s); qq = warp_sum(qq);
-  if (lane == 0) { red[warp][K] = s; red[warp][K + 1] = qq; }
+    for (int t = 0; t < K; ++t) part[t * kThreads + threadIdx.x] = gw[t];
+  }
+  if (want_s) { part[K * kThreads + threadIdx.x] = s; part[(K + 1) * kThreads + threadIdx.x] = qq; }
   __syncthreads();
-  if (threadIdx.x < K + 2) {
+  for (int v = warp; v < K + 2; v += 8) {
+    if (v < K ? !want_w : !want_s) continue;
+    const float* pv = part + v * kThreads;
     float t = 0.f;
-    for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
-    if (threadIdx.x < K) { if (J.dwd) atomicAdd(&J.dwd[c * K + threadIdx.x], t); }
-    else if (J.omode == O_BNRELU_STORE) atomicAdd(&J.bacc[(threadIdx.x - K) * P.C + c], (double)t);
+#pragma unroll
+    for (int q = 0; q < kThreads / 32; ++q) t += pv[lane + 32 * q];
+    t = warp_sum(t);
+    if (lane == 0) {
+      if (v < K) atomicAdd(&J.dwd[c * K + v], t);
+      else atomicAdd(&J.bacc[(v - K) * P.C + c], (double)t);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fused edge backward (north star (1): fused backward)
+// All depthwise candidates that write the data gradient of one edge -- the first depthwise conv of sep_conv_15 /
+// sep_conv_9 and the depthwise conv of dil_conv_15 / dil_conv_9 -- in ONE pass over the edge input: relu(x) is
+// staged once, the four transposed depthwise convolutions accumulate in shared memory, and dX is read-modify-
+// written once (was: four launches, each re-reading x and read-modify-writing dX: 16 tensor passes -> 7).
+struct EdgeBwdJob {
+  const float* du[4]; long long dubs;   // gradients wrt the depthwise outputs [B][C][Lo], order {sep15, sep9, dil15, dil9}; null = off
+  const float* wd[4];                   // [C][K]
+  float* dwd[4];                        // [C][K] atomics, or null
+  const float* x; long long xbs;        // edge input [B][C][Lin] (raw; every candidate starts with ReLU)
+  float* out; long long obs;            // dX, accumulated where x > 0
+  int Lin, Lo;
+};
+constexpr int kMaxEdgeJobs = 8;
+struct EdgeBwdBatch { int n, B, C, nseg; EdgeBwdJob j[kMaxEdgeJobs]; };
+
+template <int S>
+struct EdgeBwdGeom {
+  static constexpr int SEG = S == 1 ? 256 : 252;
+  static constexpr int XO = 16;                                    // x row: index p <-> pos = m0 - XO + p (XO >= largest pad, multiple of 4)
+  static constexpr int WX = SEG + 2 * XO + 8;
+  static constexpr int WD = S == 1 ? SEG + 2 * 14 + 16 : ((SEG + 14) / S + 15 + 4 + 3) / 4 * 4;
+  static constexpr int ROW = WX + WD + SEG;                        // floats per warp
+  static constexpr int PART = 15 * kThreads;                       // CTA reduction scratch of one candidate's taps
+};
+
+// one candidate of the fused edge backward: accumulate its dX into arow, its weight gradient into dwd
+template <int K, int D, int S>
+__device__ __forceinline__ void edge_bwd_cand(const float* dg, const float* wdp, float* dwdp, int Lo,
+                                              const float* xrow, float* drow, float* arow, float* part,
+                                              int m0, int m1, int l0, int l1, bool ok) {
+  using G = EdgeBwdGeom<S>;
+  constexpr int PADC = (K - 1) * D / 2;
+  constexpr int OFF = S == 1 ? (PADC + 3) / 4 * 4 : K;            // du row: index i <-> l = l0 - OFF + i
+  constexpr int WDV = S == 1 ? (G::SEG + 2 * PADC + 16 + 3) / 4 * 4 : ((G::SEG + PADC) / S + OFF + 4 + 3) / 4 * 4;
+  static_assert(WDV <= G::WD, "du row does not fit");
+  const int lane = threadIdx.x & 31;
+  float w[K], gw[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) { w[t] = wdp[t]; gw[t] = 0.f; }
+  __syncwarp();                                   // the previous candidate is done with drow
+  if (ok) {
+    float dv_[(WDV + 31) / 32];
+#pragma unroll
+    for (int q = 0; q < (WDV + 31) / 32; ++q) {
+      const int l = l0 - OFF + lane + 32 * q;
+      dv_[q] = (l >= 0 && l < Lo) ? dg[l] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < (WDV + 31) / 32; ++q) {
+      const int i = lane + 32 * q;
+      if (i < WDV) drow[i] = dv_[q];
+    }
+  }
+  __syncwarp();
+  if (ok) {
+    const int nm = m1 - m0, nl = l1 - l0;
+    constexpr int XS = G::XO - PADC;              // xrow index of position (l*S + t*D - pad) = (l - l0)*S + t*D + XS
+    if (S == 1) {
+      constexpr int SH = OFF - PADC;              // 0..3
+      constexpr int NW4 = ((K - 1) * D + 4 + SH + 3) / 4;
+      for (int g4 = lane; g4 * 4 < nm; g4 += 32) {
+        const int ml = g4 * 4;
+        float dw_[NW4 * 4];
+        const float4* dp = reinterpret_cast<const float4*>(drow + ml);
+#pragma unroll
+        for (int q = 0; q < NW4; ++q) { const float4 v = dp[q]; dw_[4 * q] = v.x; dw_[4 * q + 1] = v.y; dw_[4 * q + 2] = v.z; dw_[4 * q + 3] = v.w; }
+        float4 a = *reinterpret_cast<const float4*>(arow + ml);
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+          a.x = fmaf(w[t], dw_[SH + 0 + (K - 1 - t) * D], a.x); a.y = fmaf(w[t], dw_[SH + 1 + (K - 1 - t) * D], a.y);
+          a.z = fmaf(w[t], dw_[SH + 2 + (K - 1 - t) * D], a.z); a.w = fmaf(w[t], dw_[SH + 3 + (K - 1 - t) * D], a.w);
+        }
+        *reinterpret_cast<float4*>(arow + ml) = a;
+      }
+      if (dwdp) {
+        constexpr int XA = XS / 4 * 4, XR = XS - XA;          // aligned window base + in-register shift
+        constexpr int NR4 = ((K - 1) * D + 4 + XR + 3) / 4;
+        for (int g4 = lane; g4 * 4 < nl; g4 += 32) {
+          const int ll = g4 * 4;
+          const float4 dv = *reinterpret_cast<const float4*>(drow + ll + OFF);
+          const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+          float xw[NR4 * 4];
+          const float4* xp = reinterpret_cast<const float4*>(xrow + ll + XA);
+#pragma unroll
+          for (int q = 0; q < NR4; ++q) { const float4 v = xp[q]; xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w; }
+#pragma unroll
+          for (int t = 0; t < K; ++t)
+#pragma unroll
+            for (int n = 0; n < 4; ++n) gw[t] = fmaf(d4[n], xw[XR + n + t * D], gw[t]);
+        }
+      }
+    } else {
+      _Pragma("unroll 4")
+      for (int ml = lane; ml < nm; ml += 32) {
+        const int m = m0 + ml;
+        float a = arow[ml];
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+          const int num = m + PADC - t * D;
+          if (num >= 0 && num % S == 0) a = fmaf(w[t], drow[num / S - l0 + OFF], a);
+        }
+        arow[ml] = a;
+      }
+      if (dwdp) {
+        _Pragma("unroll 4")
+        for (int ll = lane; ll < nl; ll += 32) {
+          const float dv = drow[ll + OFF];
+#pragma unroll
+          for (int t = 0; t < K; ++t) gw[t] = fmaf(dv, xrow[ll * S + t * D + XS], gw[t]);
+        }
+      }
+    }
+  }
+  if (dwdp) {                                     // CTA-uniform: reduce the K taps over the 256 threads through shared memory
+    const int warp = threadIdx.x >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < K; ++t) part[t * kThreads + threadIdx.x] = gw[t];
+    __syncthreads();
+    for (int v = warp; v < K; v += 8) {
+      const float* pv = part + v * kThreads;
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < kThreads / 32; ++q) t += pv[lane + 32 * q];
+      t = warp_sum(t);
+      if (lane == 0) atomicAdd(&dwdp[v], t);
+    }
+  }
+}
+
+// CTA: channel c, 8 batch rows (one per warp), one segment of SEG input positions
+template <int S>
+__global__ void __launch_bounds__(kThreads, 3) k_edge_bwd(const __grid_constant__ EdgeBwdBatch P) {
+  using G = EdgeBwdGeom<S>;
+  constexpr int SEG = G::SEG, XO = G::XO, WX = G::WX, WD = G::WD;
+  const EdgeBwdJob& J = P.j[blockIdx.z];
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rg = blockIdx.y / P.nseg, seg = blockIdx.y - rg * P.nseg;
+  const int b = rg * 8 + warp;
+  const int m0 = seg * SEG, m1 = min(J.Lin, m0 + SEG);
+  const int l0 = m0 / S;
+  const int l1 = m1 > m0 ? min(J.Lo, (m1 - 1) / S + 1) : l0;
+  const bool ok = b < P.B && m0 < J.Lin;
+  GNAS_DYN_SMEM(float, smem);
+  float* xrow = smem + warp * G::ROW;      // relu(x) with zero halo
+  float* drow = xrow + WX;                 // du of the current candidate with zero halo
+  float* arow = drow + WD;                 // dX of the segment before masking
+  float* part = smem + 8 * G::ROW;
+  if (ok) {
+    const float* xg = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
+    float xv_[(WX + 31) / 32];
+#pragma unroll
+    for (int q = 0; q < (WX + 31) / 32; ++q) {
+      const int pos = m0 - XO + lane + 32 * q;
+      xv_[q] = (pos >= 0 && pos < J.Lin) ? xg[pos] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < (WX + 31) / 32; ++q) {
+      const int p = lane + 32 * q;
+      if (p < WX) xrow[p] = xv_[q] > 0.f ? xv_[q] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < (SEG + 31) / 32; ++q) if (lane + 32 * q < SEG) arow[lane + 32 * q] = 0.f;
+  }
+  const long long ro = (long long)(ok ? b : 0) * J.dubs + (long long)c * J.Lo;
+  if (J.du[0]) edge_bwd_cand<15, 1, S>(J.du[0] + ro, J.wd[0] + c * 15, J.dwd[0] ? J.dwd[0] + c * 15 : nullptr, J.Lo, xrow, drow, arow, part, m0, m1, l0, l1, ok);
+  if (J.du[1]) edge_bwd_cand<9, 1, S>(J.du[1] + ro, J.wd[1] + c * 9, J.dwd[1] ? J.dwd[1] + c * 9 : nullptr, J.Lo, xrow, drow, arow, part, m0, m1, l0, l1, ok);
+  if (J.du[2]) edge_bwd_cand<15, 2, S>(J.du[2] + ro, J.wd[2] + c * 15, J.dwd[2] ? J.dwd[2] + c * 15 : nullptr, J.Lo, xrow, drow, arow, part, m0, m1, l0, l1, ok);
+  if (J.du[3]) edge_bwd_cand<9, 2, S>(J.du[3] + ro, J.wd[3] + c * 9, J.dwd[3] ? J.dwd[3] + c * 9 : nullptr, J.Lo, xrow, drow, arow, part, m0, m1, l0, l1, ok);
+  __syncwarp();
+  if (ok) {
+    // one lane-interleaved read-modify-write of dX (full 128-byte lines whatever the row alignment)
+    float* orow = J.out + (long long)b * J.obs + (long long)c * J.Lin;
+    const int nm = m1 - m0;
+    _Pragma("unroll 4")
+    for (int ml = lane; ml < nm; ml += 32)
+      if (xrow[ml + XO] > 0.f) orow[m0 + ml] += arow[ml];
   }
 }
 
@@ -722,16 +910,19 @@ static __global__ void __launch_bounds__(kThreads) k_pool_bwd(const __grid_const
   const int m0 = seg * kPoolSeg, m1 = min(J.Lin, m0 + kPoolSeg);
   if (b >= P.B || m0 >= J.Lin) return;
   __shared__ float sm[8][kPoolWX + 2 * kPoolWD];
+  __shared__ int smi[8][kPoolWD];
   float* xrow = sm[warp];        // index p <-> pos = m0 - kPoolXO + p
   float* dm = xrow + kPoolWX;    // dz of the max pool, index i <-> l = m0 / S - 4 + i
   float* da = dm + kPoolWD;      // dz of the avg pool already divided by the window count
+  int* apos = smi[warp];         // position of the first maximal element of window l (torch max_pool1d backward routes there)
   const int lb = m0 / S - 4;
   const int nd = (m1 - m0 + 1) / S + 8;          // staged windows: l in [lb, lb + nd)
   const float* xg = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
   const float* gg = J.g + (long long)b * J.gbs + (long long)c * J.Lo;
   const long long zo = ((long long)b * P.C + c) * J.Lo;
+  float gv[(kPoolWD + 31) / 32], zm[(kPoolWD + 31) / 32], za[(kPoolWD + 31) / 32];
   {
-    float xv[(kPoolWX + 31) / 32], gv[(kPoolWD + 31) / 32], zm[(kPoolWD + 31) / 32], za[(kPoolWD + 31) / 32];
+    float xv[(kPoolWX + 31) / 32];
 #pragma unroll
     for (int q = 0; q < (kPoolWX + 31) / 32; ++q) {
       const int pos = m0 - kPoolXO + lane + 32 * q;
@@ -750,20 +941,32 @@ static __global__ void __launch_bounds__(kThreads) k_pool_bwd(const __grid_const
       const int p = lane + 32 * q;
       if (p < kPoolWX) xrow[p] = xv[q];
     }
+  }
+  __syncwarp();
 #pragma unroll
-    for (int q = 0; q < (kPoolWD + 31) / 32; ++q) {
-      const int i = lane + 32 * q, l = lb + i;
-      if (i < kPoolWD) {
-        float vm = 0.f, va = 0.f;
-        if (i < nd && l >= 0 && l < J.Lo) {
-          if (J.zmax) vm = fmaf(J.coef_max[c], gv[q], fmaf(J.coef_max[P.C + c], zm[q], J.coef_max[2 * P.C + c]));
-          if (J.zavg) {
-            const int lo = max(l * S - 2, 0), hi = min(l * S + 2, J.Lin - 1);
-            va = fmaf(J.coef_avg[c], gv[q], fmaf(J.coef_avg[P.C + c], za[q], J.coef_avg[2 * P.C + c])) / (float)(hi - lo + 1);
+  for (int q = 0; q < (kPoolWD + 31) / 32; ++q) {
+    const int i = lane + 32 * q, l = lb + i;
+    if (i < kPoolWD) {
+      float vm = 0.f, va = 0.f;
+      int ap = -1;
+      if (i < nd && l >= 0 && l < J.Lo) {
+        if (J.zmax) {
+          vm = fmaf(J.coef_max[c], gv[q], fmaf(J.coef_max[P.C + c], zm[q], J.coef_max[2 * P.C + c]));
+          const int p0 = l * S - 2 - m0 + kPoolXO;           // xrow index of pos l*S-2; staged windows keep it in range
+          if (p0 >= 0 && p0 + 4 < kPoolWX) {
+            const float* wv = xrow + p0;
+            int am = 0; float best = wv[0];
+#pragma unroll
+            for (int t = 1; t < 5; ++t) if (wv[t] > best) { best = wv[t]; am = t; }
+            ap = l * S - 2 + am;
           }
         }
-        dm[i] = vm; da[i] = va;
+        if (J.zavg) {
+          const int lo = max(l * S - 2, 0), hi = min(l * S + 2, J.Lin - 1);
+          va = fmaf(J.coef_avg[c], gv[q], fmaf(J.coef_avg[P.C + c], za[q], J.coef_avg[2 * P.C + c])) / (float)(hi - lo + 1);
+        }
       }
+      dm[i] = vm; da[i] = va; apos[i] = ap;
     }
   }
   __syncwarp();
@@ -777,19 +980,12 @@ static __global__ void __launch_bounds__(kThreads) k_pool_bwd(const __grid_const
     int l_hi = (m + 2) / S; if (l_hi > J.Lo - 1) l_hi = J.Lo - 1;
     for (int l = l_lo; l <= l_hi; ++l) {
       a += da[l - lb];
-      if (J.zmax) {
-        // first maximal element of window l (torch max_pool1d backward routes there)
-        const float* wv = xrow + (l * S - 2 - m0 + kPoolXO);   // index 0 <-> pos l*S-2
-        int am = 0; float best = wv[0];
-#pragma unroll
-        for (int t = 1; t < 5; ++t) if (wv[t] > best) { best = wv[t]; am = t; }
-        if (l * S - 2 + am == m) a += dm[l - lb];
-      }
+      if (apos[l - lb] == m) a += dm[l - lb];
     }
     if (J.skip_widx >= 0) {
-      float gv = gg[m] * wskip;
-      if (J.skip_mask) gv *= J.skip_mask[((long long)b * P.C + c) * J.Lin + m];
-      a += gv;
+      float gs = gg[m] * wskip;
+      if (J.skip_mask) gs *= J.skip_mask[((long long)b * P.C + c) * J.Lin + m];
+      a += gs;
     }
     drow[m] += a;
   }

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwB
   constexpr int NX = 3 * S + (K - 1) * D + 1;
   constexpr int NX4 = (NX + 3) / 4;
   __shared__ __align__(16) float rows[8][WP];
+  __shared__ __align__(16) float outs[8][SEGO];
   float* row = rows[warp];
   if (c >= P.C || l0 >= J.Lout) return;
   {
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwB
   for (int t = 0; t < K; ++t) w[t] = J.wd[c * K + t];
   float* ur = J.u + (long long)b * J.ubs + (long long)c * J.Lout;
   const bool vecok = (J.Lout % 4 == 0) && (J.ubs % 4 == 0);
+  float* orow = outs[warp];
   for (int g = lane; l0 + g * 4 < l1; g += 32) {
     const int l = l0 + g * 4;
     float xw[NX4 * 4];
@@ -263,9 +265,14 @@ __global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwB
     for (int t = 0; t < K; ++t)
 #pragma unroll
       for (int n = 0; n < 4; ++n) a[n] = fmaf(w[t], xw[n * S + t * D], a[n]);
-    if (vecok && l + 3 < J.Lout) *reinterpret_cast<float4*>(ur + l) = make_float4(a[0], a[1], a[2], a[3]);
-    else
-      for (int n = 0; n < 4; ++n) if (l + n < J.Lout) ur[l + n] = a[n];
+    if (vecok) *reinterpret_cast<float4*>(ur + l) = make_float4(a[0], a[1], a[2], a[3]);     // Lout % 4 == 0: l + 3 < Lout
+    else *reinterpret_cast<float4*>(orow + g * 4) = make_float4(a[0], a[1], a[2], a[3]);
+  }
+  if (!vecok) {
+    // rows that are not 16-byte aligned (L = 250, 125, 42): lane-interleaved stores, one full line per warp request
+    __syncwarp();
+    _Pragma("unroll 4")
+    for (int l = l0 + lane; l < l1; l += 32) ur[l] = orow[l - l0];
   }
 }
 

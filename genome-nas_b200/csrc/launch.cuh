@@ -52,7 +52,12 @@ static void launch_dense_fwd_t(DenseBatch& b, int maxLout, cudaStream_t st) {
 }
 template <int KW, int S>
 static void launch_dense_fwd_s(DenseBatch& b, int maxLout, cudaStream_t st) {
-  switch (choose_tm(b.Cout)) {
+  int tm = choose_tm(b.Cout);
+  // 1x1 convolutions (preprocess, FactorizedReduce) have no arithmetic to amortise: narrower register tiles give
+  // shorter position tiles and hence more CTAs (TM = 8 left cells 2-5 with 64 CTAs of ~90 us on 148 SMs)
+  if (KW == 1)
+    while (tm > 2 && (long long)cdiv(maxLout, 4 * (kThreads / (b.Cout / tm))) * b.B * b.n < 2 * 148) tm >>= 1;
+  switch (tm) {
     case 8: launch_dense_fwd_t<KW, S, 8>(b, maxLout, st); break;
     case 4: launch_dense_fwd_t<KW, S, 4>(b, maxLout, st); break;
     default: launch_dense_fwd_t<KW, S, 2>(b, maxLout, st); break;
@@ -241,7 +246,7 @@ static void launch_dw_bwd_t(DwBwdBatch& b, cudaStream_t st) {
   int lin = 1;
   for (int i = 0; i < b.n; ++i) lin = b.j[i].Lin > lin ? b.j[i].Lin : lin;
   b.nseg = cdiv(lin, G::SEG);
-  const size_t smem = sizeof(float) * 8 * (size_t)(G::WX + G::WD);
+  const size_t smem = sizeof(float) * 8 * (size_t)(G::WX + G::WD + G::SEG);
   GNAS_PREP_SMEM((k_dw_bwd<K, D, S>), smem);
   // rows per warp: reduce the per-row reduction/atomic overhead only when the grid is far larger than the machine
   int rpw = (b.C * cdiv(b.B, 8) * b.n * b.nseg) / (16 * 148);
@@ -260,6 +265,28 @@ static int launch_dw_bwd(int K, int D, int S, DwBwdBatch& b, cudaStream_t st) {
   GNAS_DW_CASE(9, 2, 1) GNAS_DW_CASE(9, 2, 2) GNAS_DW_CASE(9, 2, 3)
   { set_error("dw_bwd: unsupported (K, D, S)"); return GNAS_ERR_UNSUPPORTED; }
 #undef GNAS_DW_CASE
+  b.n = 0;
+  return 0;
+}
+
+// ------------------------------------------------------------------ fused edge backward
+template <int S>
+static void launch_edge_bwd_t(EdgeBwdBatch& b, cudaStream_t st) {
+  using G = EdgeBwdGeom<S>;
+  int lin = 1;
+  for (int i = 0; i < b.n; ++i) lin = b.j[i].Lin > lin ? b.j[i].Lin : lin;
+  b.nseg = cdiv(lin, G::SEG);
+  const size_t smem = sizeof(float) * (8 * (size_t)G::ROW + G::PART);
+  GNAS_PREP_SMEM((k_edge_bwd<S>), smem);
+  dim3 grid(b.C, cdiv(b.B, 8) * b.nseg, b.n);
+  GNAS_LAUNCH((k_edge_bwd<S>), grid, dim3(kThreads), smem, st, b);
+}
+static int launch_edge_bwd(int S, EdgeBwdBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  if (S == 1) launch_edge_bwd_t<1>(b, st);
+  else if (S == 2) launch_edge_bwd_t<2>(b, st);
+  else if (S == 3) launch_edge_bwd_t<3>(b, st);
+  else { set_error("edge_bwd: unsupported stride"); return GNAS_ERR_UNSUPPORTED; }
   b.n = 0;
   return 0;
 }

@@ -35,6 +35,13 @@ def run():
 for _ in range(2):
     m.zero_grad(); run()
 torch.cuda.synchronize()
+# wall time of a forward + backward pass (CUDA events, no per-launch bracketing): what the side-stream overlap changes
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    m.zero_grad(); run()
+e1.record(); torch.cuda.synchronize()
+print(f"SIDE={os.environ.get('GNAS_RHN_SIDE', '1')} fwd+bwd wall {e0.elapsed_time(e1) / 5:.3f} ms/pass")
 _lib.profile(True)
 n = 3
 for _ in range(n):
