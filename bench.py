@@ -273,10 +273,12 @@ def algorithmic_work(B, sw_normal, sw_reduce, T=42, H=512, n_rnn_edges=36):
                 w["pw_wg"] += n_pw * 2.0 * B * C * C * Lo
                 n_dw1 = on('sep_conv_15') + on('sep_conv_9') + on('dil_conv_15') + on('dil_conv_9')
                 n_dw2 = on('sep_conv_15') + on('sep_conv_9')
-                # depthwise forward: read the input once, write the output once
-                w["dw_fwd_b"] += 2 * (n_dw1 * (el_i + el_o) + n_dw2 * 2 * el_o)
-                # depthwise backward: read du and the forward input (ReLU mask / weight gradient), write dx
-                w["dw_bwd_b"] += 2 * (n_dw1 * (el_o + 2 * el_i) + n_dw2 * 3 * el_o)
+                # depthwise forward (fused per edge): read the edge input once, write one output per candidate;
+                # second stage of sep_conv: read z1, write u2
+                w["dw_fwd_b"] += 2 * ((el_i if n_dw1 else 0) + n_dw1 * el_o + n_dw2 * 2 * el_o)
+                # depthwise backward (fused per edge): read every candidate's du and the edge input once,
+                # read-modify-write dX once; second stage of sep_conv: read du2 and z1, write dyh1
+                w["dw_bwd_b"] += 2 * (n_dw1 * el_o + (3 * el_i if n_dw1 else 0) + n_dw2 * 3 * el_o)
                 n_pool = on('max_pool_5') + on('avg_pool_5')
                 if n_pool:
                     w["pool_fwd_b"] += 2 * (el_i + n_pool * el_o)

@@ -302,7 +302,24 @@ struct Ctx {
   const int64_t* skip_mask;
   float* out; float* ws; float* scratch;
   cudaStream_t st;
+  SideStream wside = {nullptr, nullptr, {nullptr, nullptr}};   // weight-gradient kernels are leaves of the backward pass: they run beside the data-gradient chain
+  bool wforked = false;
   int rc = 0;
+  // stream for a weight-gradient launch whose inputs are complete on `st` at this point
+  cudaStream_t wg_stream() {
+    if (!wside.st) return st;
+    cudaEventRecord(wside.fork, st);
+    cudaStreamWaitEvent(wside.st, wside.fork, 0);
+    wforked = true;
+    return wside.st;
+  }
+  // before anything the forked launches read (edge temporaries) is overwritten, and before the call returns
+  void wg_join() {
+    if (!wforked) return;
+    cudaEventRecord(wside.join[0], wside.st);
+    cudaStreamWaitEvent(st, wside.join[0], 0);
+    wforked = false;
+  }
 
   const float* W(int e, int k, int i) const { return params + d->w_off[e][k][i]; }
   float* dW(int e, int k, int i) const { return grads + d->w_off[e][k][i]; }
@@ -351,6 +368,8 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
   auto fin_add = [&](int e, int k, int which) {
     fs[nf] = c.P.e[e].op[k].slot[which]; fc[nf] = (float)((long long)B * Lo); fr[nf] = d->bn_off[e][k][which]; ++nf;
   };
+  // the conv_15 chain reads only the edge sources: it runs on the side stream, forked here, beside pools / depthwise / pointwise
+  cudaStream_t cst = c.wg_stream();
   // ---- stage 1
   {
     PoolBatch pb; pb.n = 0; pb.B = B; pb.C = C; pb.S = S;
@@ -389,17 +408,23 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
   // depthwise stage 1 (sep: dilation 1, dil: dilation 2)
   const int dwk[4] = {GNAS_SEP15, GNAS_SEP9, GNAS_DIL15, GNAS_DIL9};
   const int dwK[4] = {15, 9, 15, 9}, dwD[4] = {1, 1, 2, 2}, dwP[4] = {7, 4, 14, 8};
-  for (int v = 0; v < 4; ++v) {
-    DwBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = dwP[v];
+  {   // fused: one pass over relu(x) per edge for all four candidates
+    EdgeFwdBatch eb; eb.n = 0; eb.B = B; eb.C = C;
     for (int i = 0; i < ne; ++i) {
       const int e = edges[i];
-      if (!c.P.e[e].op[dwk[v]].on) continue;
-      DwJob& j = wb.j[wb.n++];
-      c.src(e, j.x, j.xbs); j.in_stat = nullptr; j.wd = c.W(e, dwk[v], 0);
-      j.u = c.T(e, dwk[v], 0); j.ubs = obs; j.Lin = Lin; j.Lout = Lo; j.tin = T_RELU;
-      if (wb.n == kMaxDw) c.rc |= launch_dw_fwd(dwK[v], dwD[v], S, wb, c.st);
+      bool any = false;
+      for (int v = 0; v < 4; ++v) any = any || c.P.e[e].op[dwk[v]].on;
+      if (!any) continue;
+      EdgeFwdJob& j = eb.j[eb.n++];
+      c.src(e, j.x, j.xbs); j.ubs = obs; j.Lin = Lin; j.Lout = Lo;
+      for (int v = 0; v < 4; ++v) {
+        const bool on = c.P.e[e].op[dwk[v]].on;
+        j.wd[v] = on ? c.W(e, dwk[v], 0) : nullptr;
+        j.u[v] = on ? c.T(e, dwk[v], 0) : nullptr;
+      }
+      if (eb.n == kMaxEdgeFwd) c.rc |= launch_edge_fwd(S, eb, c.st);
     }
-    c.rc |= launch_dw_fwd(dwK[v], dwD[v], S, wb, c.st);
+    c.rc |= launch_edge_fwd(S, eb, c.st);
   }
   // pointwise stage 1
   for (int i = 0; i < ne; ++i) {
@@ -416,7 +441,8 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     }
   }
   c.rc |= pw_fwd(db);
-  // conv_15 stage 1
+  // conv_15 stage 1 (independent of the depthwise / pointwise chain: runs beside it on the side stream; the stream
+  // was forked at the top of the function, the kernels above were enqueued on c.st in the meantime)
   db.pad = 7;
   for (int i = 0; i < ne; ++i) {
     const int e = edges[i];
@@ -428,10 +454,12 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     j.Cin = C; j.Lin = Lin; j.Lout = Lo; j.tin = T_RELU;
     fin_add(e, GNAS_CONV15, 0);
   }
-  c.rc |= tc_fwd_on(C, S) ? launch_conv_fwd_tc(db, 15, c.st)
-          : (S > 1 && tc_sfw_on(C, S)) ? launch_conv_fwd_strided_tc(db, S, c.st) : launch_dense_fwd(15, S, db, c.st);
+  c.rc |= tc_fwd_on(C, S) ? launch_conv_fwd_tc(db, 15, cst)
+          : (S > 1 && tc_sfw_on(C, S)) ? launch_conv_fwd_strided_tc(db, S, cst) : launch_dense_fwd(15, S, db, cst);
+  c.wg_join();
   finalize(c, fs, fc, fr, nf);
   nf = 0;
+  cst = c.wg_stream();
   // ---- stage 2 (sep_conv second half, conv_15 second conv) reads BN+ReLU of stage 1 on the fly
   for (int v = 0; v < 2; ++v) {
     DwBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = dwP[v];
@@ -471,7 +499,8 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     j.Cin = C; j.Lin = Lo; j.Lout = Lo; j.tin = T_BN_RELU;
     fin_add(e, GNAS_CONV15, 1);
   }
-  c.rc |= tc_fwd_on(C, 1) ? launch_conv_fwd_tc(db, 15, c.st) : launch_dense_fwd(15, 1, db, c.st);
+  c.rc |= tc_fwd_on(C, 1) ? launch_conv_fwd_tc(db, 15, cst) : launch_dense_fwd(15, 1, db, cst);
+  c.wg_join();
   finalize(c, fs, fc, fr, nf);
 }
 
@@ -694,13 +723,19 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     auto pw_dx = [&](DxBatch& b) { return tc_pw_on(C) ? launch_conv_dx_tc(b, 1, c.st) : launch_dense_dx(1, 1, b, c.st); };
     auto conv_wg = [&](WgBatch& b, int stride) {
 #ifndef GNAS_EMUL
-      if (tc_enabled() && tc_part(stride == 1 ? 5 : 8) && tc::conv_wgrad_tc_supported(b, stride)) return tc::launch_conv_wgrad_tc(b, stride, c.st);
+      if (b.n == 0) return 0;
+      cudaStream_t ws_ = c.wg_stream();
+      if (tc_enabled() && tc_part(stride == 1 ? 5 : 8) && tc::conv_wgrad_tc_supported(b, stride)) return tc::launch_conv_wgrad_tc(b, stride, ws_);
+      return launch_conv_wgrad(15, stride, 7, b, ws_);
 #endif
       return launch_conv_wgrad(15, stride, 7, b, c.st);
     };
     auto pw_wg = [&](WgBatch& b) {
 #ifndef GNAS_EMUL
-      if (tc_enabled() && tc_part(4) && tc::pw_wgrad_tc_supported(b)) return tc::launch_pw_wgrad_tc(b, c.st);
+      if (b.n == 0) return 0;
+      cudaStream_t ws_ = c.wg_stream();
+      if (tc_enabled() && tc_part(4) && tc::pw_wgrad_tc_supported(b)) return tc::launch_pw_wgrad_tc(b, ws_);
+      return launch_pw_wgrad(1, b, ws_);
 #endif
       return launch_pw_wgrad(1, b, c.st);
     };
@@ -723,7 +758,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         }
       }
       c.rc |= launch_dense_dx(1, S, xb, c.st);
-      c.rc |= launch_pw_wgrad(S, gb, c.st);
+      if (gb.n) c.rc |= launch_pw_wgrad(S, gb, c.wg_stream());
     }
     // -- last pointwise conv of sep (stage 2) and dil: du = W^T dz, dWpw
     for (int i = 0; i < n2; ++i) {
@@ -864,6 +899,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
             : (S > 1 && tc_sdx_on(C, S)) ? launch_conv_dx_strided_tc(xb, S, c.st) : launch_dense_dx(15, S, xb, c.st);
     c.rc |= conv_wg(gb, S);
   }
+  c.wg_join();      // the next node reuses the edge temporaries the forked weight-gradient kernels read
 }
 
 void preprocess_backward(Ctx& c, float* ds0, float* ds1, int need_wgrad) {
@@ -992,6 +1028,7 @@ extern "C" int gnas_cell_forward(const GnasCellDesc* d, const float* params, flo
   c.d = d; make_plan(d, c.P);
   c.params = params; c.grads = nullptr; c.running = bn_running; c.s0 = s0; c.s1 = s1; c.mixw = mixw;
   c.skip_mask = skip_mask_host; c.out = out; c.ws = ws; c.scratch = nullptr; c.st = (cudaStream_t)stream;
+  c.wside = side_stream(1);
   if (d->training)
     cudaMemsetAsync(ws + c.P.acc, 0, sizeof(double) * (size_t)c.P.nslots * 2 * d->C, c.st);
   pack_forward(c);
@@ -1038,6 +1075,7 @@ extern "C" int gnas_cell_backward(const GnasCellDesc* d, const float* params, fl
   c.params = params; c.grads = grads; c.running = nullptr; c.s0 = s0; c.s1 = s1; c.mixw = mixw;
   c.skip_mask = skip_mask_host; c.out = const_cast<float*>(out); c.ws = const_cast<float*>(ws); c.scratch = scratch;
   c.st = (cudaStream_t)stream;
+  c.wside = side_stream(need_wgrad ? 1 : -1);
   const int C = d->C, B = d->B, Lo = d->L_out;
   const long long obs = (long long)C * Lo;
   // bacc | dmix | coef sit at the head of the scratch: zero the accumulators

@@ -276,6 +276,96 @@ __global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwB
   }
 }
 
+// ------------------------------------------------------------------ fused edge forward (north star (1))
+// The first depthwise convolution of every enabled sep_conv / dil_conv candidate of one edge in ONE pass:
+// relu(x) is staged once per (row, segment) tile and each candidate writes its own output (was: one launch per
+// candidate, each re-reading and re-transforming x).
+struct EdgeFwdJob {
+  const float* x; long long xbs;      // edge input [B][C][Lin]
+  const float* wd[4];                 // [C][K], order {sep15, sep9, dil15, dil9}; null = candidate off
+  float* u[4]; long long ubs;         // outputs [B][C][Lout]
+  int Lin, Lout;
+};
+constexpr int kMaxEdgeFwd = 8;
+struct EdgeFwdBatch { int n, B, C, nseg; EdgeFwdJob j[kMaxEdgeFwd]; };
+template <int S>
+struct EdgeFwdGeom {
+  static constexpr int SEGO = S == 1 ? 256 : (S == 2 ? 128 : 84);
+  static constexpr int XO = 16;                                                  // row: index p <-> pos = l0*S - XO + p
+  static constexpr int WP = (SEGO * S + 2 * XO + 3 * S + 8 + 3) / 4 * 4;
+};
+
+template <int K, int D, int S>
+__device__ __forceinline__ void edge_fwd_cand(const float* row, const float* wdp, float* ur, float* orow, int l0, int l1,
+                                              int Lout, bool vecok) {
+  using G = EdgeFwdGeom<S>;
+  constexpr int PADC = (K - 1) * D / 2;
+  constexpr int XS = G::XO - PADC, XA = XS / 4 * 4, XR = XS - XA;
+  constexpr int NX4 = (3 * S + (K - 1) * D + 1 + XR + 3) / 4;
+  const int lane = threadIdx.x & 31;
+  float w[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) w[t] = wdp[t];
+  __syncwarp();                                   // the previous candidate's staged outputs have been stored
+  for (int g = lane; l0 + g * 4 < l1; g += 32) {
+    const int l = l0 + g * 4;
+    float xw[NX4 * 4];
+    const float4* xp = reinterpret_cast<const float4*>(row + g * 4 * S + XA);
+#pragma unroll
+    for (int q = 0; q < NX4; ++q) { float4 v = xp[q]; xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w; }
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < K; ++t)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) a[n] = fmaf(w[t], xw[XR + n * S + t * D], a[n]);
+    if (vecok) *reinterpret_cast<float4*>(ur + l) = make_float4(a[0], a[1], a[2], a[3]);
+    else *reinterpret_cast<float4*>(orow + g * 4) = make_float4(a[0], a[1], a[2], a[3]);
+  }
+  if (!vecok) {
+    __syncwarp();
+    _Pragma("unroll 4")
+    for (int l = l0 + lane; l < l1; l += 32) ur[l] = orow[l - l0];
+  }
+  (void)Lout;
+}
+
+// CTA: batch row b, 8 channels (one per warp), one output segment
+template <int S>
+__global__ void __launch_bounds__(kThreads) k_edge_fwd(const __grid_constant__ EdgeFwdBatch P) {
+  using G = EdgeFwdGeom<S>;
+  constexpr int SEGO = G::SEGO, WP = G::WP, XO = G::XO;
+  const EdgeFwdJob& J = P.j[blockIdx.z];
+  const int b = blockIdx.y / P.nseg, seg = blockIdx.y - b * P.nseg;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 8 + warp;
+  const int l0 = seg * SEGO, l1 = min(J.Lout, l0 + SEGO);
+  __shared__ __align__(16) float rows[8][WP];
+  __shared__ __align__(16) float outs[8][SEGO];
+  if (c >= P.C || l0 >= J.Lout) return;
+  float* row = rows[warp];
+  {
+    const float* xr = J.x + (long long)b * J.xbs + (long long)c * J.Lin;
+    float xv[(WP + 31) / 32];
+#pragma unroll
+    for (int q = 0; q < (WP + 31) / 32; ++q) {
+      const int pos = l0 * S - XO + lane + 32 * q;
+      xv[q] = (pos >= 0 && pos < J.Lin) ? xr[pos] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < (WP + 31) / 32; ++q) {
+      const int p = lane + 32 * q;
+      if (p < WP) row[p] = xv[q] > 0.f ? xv[q] : 0.f;
+    }
+  }
+  __syncwarp();
+  const bool vecok = (J.Lout % 4 == 0) && (J.ubs % 4 == 0);
+  const long long uo = (long long)b * J.ubs + (long long)c * J.Lout;
+  if (J.wd[0]) edge_fwd_cand<15, 1, S>(row, J.wd[0] + c * 15, J.u[0] + uo, outs[warp], l0, l1, J.Lout, vecok);
+  if (J.wd[1]) edge_fwd_cand<9, 1, S>(row, J.wd[1] + c * 9, J.u[1] + uo, outs[warp], l0, l1, J.Lout, vecok);
+  if (J.wd[2]) edge_fwd_cand<15, 2, S>(row, J.wd[2] + c * 15, J.u[2] + uo, outs[warp], l0, l1, J.Lout, vecok);
+  if (J.wd[3]) edge_fwd_cand<9, 2, S>(row, J.wd[3] + c * 9, J.u[3] + uo, outs[warp], l0, l1, J.Lout, vecok);
+}
+
 // ------------------------------------------------------------------ pools
 struct PoolJob {
   const float* x; long long xbs;

@@ -115,6 +115,18 @@ static inline bool need_prepare(int* table, int want) {
 }
 #endif
 
+// A second stream per device and purpose for work that is off the critical path of a backward pass (fork / join by
+// events, which a CUDA-graph capture of the caller's stream records as plain dependencies).  `which`: 0 = RHN
+// backward products (GNAS_RHN_SIDE=0 disables), 1 = cell weight gradients (GNAS_WG_SIDE=0 disables).  st == nullptr:
+// not available (emulator, disabled, stream creation failed) -- callers then stay on their own stream.
+#ifdef GNAS_EMUL      // the emulator has one in-order queue: these are never called
+typedef void* cudaEvent_t;
+static inline int cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline int cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return 0; }
+#endif
+struct SideStream { cudaStream_t st; cudaEvent_t fork; cudaEvent_t join[2]; };
+SideStream side_stream(int which);
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return cdiv(a, b) * b; }

@@ -269,6 +269,25 @@ static int launch_dw_bwd(int K, int D, int S, DwBwdBatch& b, cudaStream_t st) {
   return 0;
 }
 
+// ------------------------------------------------------------------ fused edge forward
+template <int S>
+static void launch_edge_fwd_t(EdgeFwdBatch& b, cudaStream_t st) {
+  int lout = 1;
+  for (int i = 0; i < b.n; ++i) lout = b.j[i].Lout > lout ? b.j[i].Lout : lout;
+  b.nseg = cdiv(lout, EdgeFwdGeom<S>::SEGO);
+  dim3 grid(cdiv(b.C, 8), b.B * b.nseg, b.n);
+  GNAS_LAUNCH((k_edge_fwd<S>), grid, dim3(kThreads), 0, st, b);
+}
+static int launch_edge_fwd(int S, EdgeFwdBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  if (S == 1) launch_edge_fwd_t<1>(b, st);
+  else if (S == 2) launch_edge_fwd_t<2>(b, st);
+  else if (S == 3) launch_edge_fwd_t<3>(b, st);
+  else { set_error("edge_fwd: unsupported stride"); return GNAS_ERR_UNSUPPORTED; }
+  b.n = 0;
+  return 0;
+}
+
 // ------------------------------------------------------------------ fused edge backward
 template <int S>
 static void launch_edge_bwd_t(EdgeBwdBatch& b, cudaStream_t st) {

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/gnas.h"
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -34,6 +35,33 @@ std::string tidy(const char* kernel, const char* where) {
   return k;
 }
 }  // namespace
+
+SideStream side_stream(int which) {
+  SideStream none; none.st = nullptr; none.fork = nullptr; none.join[0] = none.join[1] = nullptr;
+#ifdef GNAS_EMUL
+  (void)which;
+  return none;
+#else
+  constexpr int kWhich = 2;
+  static SideStream table[kWhich][kMaxDevices];
+  static bool made[kWhich][kMaxDevices] = {{false}};
+  static int enabled[kWhich] = {-1, -1};
+  if (which < 0 || which >= kWhich) return none;
+  if (enabled[which] < 0) { const char* e = getenv(which == 0 ? "GNAS_RHN_SIDE" : "GNAS_WG_SIDE"); enabled[which] = e ? atoi(e) : 1; }
+  int dev = 0;
+  if (!enabled[which] || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return none;
+  if (!made[which][dev]) {
+    SideStream s;
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return none;
+    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.join[1], cudaEventDisableTiming);
+    table[which][dev] = s;
+    made[which][dev] = true;
+  }
+  return table[which][dev];
+#endif
+}
 
 void prof_before(const char* kernel, const char* where, cudaStream_t stream) {
   ++g_launches;

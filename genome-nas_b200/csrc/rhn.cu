@@ -950,38 +950,6 @@ extern "C" int gnas_rhn_forward(const GnasRhnDesc* d, const float* x, const floa
   return check_launch("gnas_rhn_forward");
 }
 
-// A second stream per device for the off-critical-path products of the backward recurrence (fork / join by events,
-// which a CUDA-graph capture of the caller's stream records as plain dependencies).  GNAS_RHN_SIDE=0 disables it.
-#ifdef GNAS_EMUL      // the emulator has one in-order queue: the side stream is never created, these are never called
-typedef void* cudaEvent_t;
-static inline int cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
-static inline int cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return 0; }
-#endif
-struct SideStream { cudaStream_t st; cudaEvent_t fork; cudaEvent_t join[2]; };
-static SideStream side_stream() {
-  SideStream none; none.st = nullptr; none.fork = nullptr; none.join[0] = none.join[1] = nullptr;
-#ifdef GNAS_EMUL
-  return none;
-#else
-  static SideStream table[kMaxDevices];
-  static bool made[kMaxDevices] = {false};
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("GNAS_RHN_SIDE"); enabled = e ? atoi(e) : 1; }
-  int dev = 0;
-  if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return none;
-  if (!made[dev]) {
-    SideStream s;
-    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return none;
-    cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s.join[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&s.join[1], cudaEventDisableTiming);
-    table[dev] = s;
-    made[dev] = true;
-  }
-  return table[dev];
-#endif
-}
-
 extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const float* h0, const float* W0,
                                  const float* Ws, const float* probs, const float* x_mask, const float* h_mask,
                                  const float* dout, float* ws, float* scratch, float* dx, float* dh0,
@@ -1025,7 +993,7 @@ extern "C" int gnas_rhn_backward(const GnasRhnDesc* d, const float* x, const flo
     if (need_prepare(prepared, (int)gsm)) cudaFuncSetAttribute(k_rhn_bwd_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm); }
 #endif
   if (nch_g > 4 || nch_g < 1) { set_error("rhn_backward: unsupported hidden size for the GEMM split"); return GNAS_ERR_UNSUPPORTED; }
-  const SideStream side = side_stream();
+  const SideStream side = side_stream(0);
   for (int t = T - 1; t >= 0; --t) {
     float* dh_cur = dhbuf[(T - 1 - t) & 1];
     float* dh_next = dhbuf[(T - t) & 1];

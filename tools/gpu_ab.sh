@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
-CHECK=0 GNAS_RHN_SIDE=1 timeout 300 python tools/rhn_bench.py > gpurun_out/r2_rhn_side1.txt 2>&1; head -1 gpurun_out/r2_rhn_side1.txt
-CHECK=0 GNAS_RHN_SIDE=0 timeout 300 python tools/rhn_bench.py > gpurun_out/r2_rhn_side0.txt 2>&1; head -1 gpurun_out/r2_rhn_side0.txt
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -1 gpurun_out/bench.log | cut -c1-300; tail -3 gpurun_out/bench.err
-GNAS_RHN_SIDE=0 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/bench_side0.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -1 gpurun_out/bench_side0.log | cut -c1-300
+GNAS_WG_SIDE=0 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/bench_wg0.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -1 gpurun_out/bench_wg0.log | cut -c1-300
