@@ -302,24 +302,32 @@ struct Ctx {
   const int64_t* skip_mask;
   float* out; float* ws; float* scratch;
   cudaStream_t st;
-  SideStream wside = {nullptr, nullptr, {nullptr, nullptr}};   // weight-gradient kernels are leaves of the backward pass: they run beside the data-gradient chain
-  bool wforked = false;
+  // Independent chains of a cell pass run beside the main chain on side streams (fork / join by events; a CUDA-graph
+  // capture records them as plain dependencies): 1 = weight-gradient kernels (leaves of the backward pass) and the
+  // conv_15 forward chain, 2 = pools / strided skip (forward) and the pool / skip data gradients (backward),
+  // 3 = the data gradient of the second conv_15 convolution.
+  SideStream side[4] = {{nullptr, nullptr, {nullptr, nullptr}}, {nullptr, nullptr, {nullptr, nullptr}},
+                        {nullptr, nullptr, {nullptr, nullptr}}, {nullptr, nullptr, {nullptr, nullptr}}};
+  bool forked[4] = {false, false, false, false};
   int rc = 0;
-  // stream for a weight-gradient launch whose inputs are complete on `st` at this point
-  cudaStream_t wg_stream() {
-    if (!wside.st) return st;
-    cudaEventRecord(wside.fork, st);
-    cudaStreamWaitEvent(wside.st, wside.fork, 0);
-    wforked = true;
-    return wside.st;
+  void init_sides(bool on) { for (int w = 1; w < 4; ++w) side[w] = side_stream(on ? w : -1); }
+  // stream for a launch whose inputs are complete on `st` at this point
+  cudaStream_t fork(int w) {
+    if (!side[w].st) return st;
+    cudaEventRecord(side[w].fork, st);
+    cudaStreamWaitEvent(side[w].st, side[w].fork, 0);
+    forked[w] = true;
+    return side[w].st;
   }
-  // before anything the forked launches read (edge temporaries) is overwritten, and before the call returns
-  void wg_join() {
-    if (!wforked) return;
-    cudaEventRecord(wside.join[0], wside.st);
-    cudaStreamWaitEvent(st, wside.join[0], 0);
-    wforked = false;
+  // before anything the forked launches read is overwritten / anything they write is consumed, and before the call returns
+  void join(int w) {
+    if (!forked[w]) return;
+    cudaEventRecord(side[w].join[0], side[w].st);
+    cudaStreamWaitEvent(st, side[w].join[0], 0);
+    forked[w] = false;
   }
+  cudaStream_t wg_stream() { return fork(1); }
+  void wg_join() { join(1); }
 
   const float* W(int e, int k, int i) const { return params + d->w_off[e][k][i]; }
   float* dW(int e, int k, int i) const { return grads + d->w_off[e][k][i]; }
@@ -369,7 +377,8 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     fs[nf] = c.P.e[e].op[k].slot[which]; fc[nf] = (float)((long long)B * Lo); fr[nf] = d->bn_off[e][k][which]; ++nf;
   };
   // the conv_15 chain reads only the edge sources: it runs on the side stream, forked here, beside pools / depthwise / pointwise
-  cudaStream_t cst = c.wg_stream();
+  cudaStream_t cst = c.fork(1);
+  cudaStream_t pst = c.fork(2);       // pools and the strided skip: short kernels on the edge sources, beside both chains
   // ---- stage 1
   {
     PoolBatch pb; pb.n = 0; pb.B = B; pb.C = C; pb.S = S;
@@ -386,9 +395,9 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
       j.Lin = Lin; j.Lout = Lo;
       if (mx.on) fin_add(e, GNAS_MAX_POOL, 0);
       if (av.on) fin_add(e, GNAS_AVG_POOL, 0);
-      if (pb.n == kMaxPool) launch_pool_fwd(pb, c.st);
+      if (pb.n == kMaxPool) launch_pool_fwd(pb, pst);
     }
-    launch_pool_fwd(pb, c.st);
+    launch_pool_fwd(pb, pst);
   }
   DenseBatch db; db.n = 0; db.B = B; db.Cout = C; db.pad = 0;
   if (S > 1) {  // strided skip = FactorizedReduce (both halves read the same positions: quirk Q4)
@@ -402,7 +411,7 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
       j.Cin = C; j.Lin = Lin; j.Lout = Lo; j.tin = T_RELU;
       fin_add(e, GNAS_SKIP, 0);
     }
-    c.rc |= launch_dense_fwd(1, S, db, c.st);
+    c.rc |= launch_dense_fwd(1, S, db, pst);
   }
   auto pw_fwd = [&](DenseBatch& b) { return tc_pw_on(C) ? launch_conv_fwd_tc(b, 1, c.st) : launch_dense_fwd(1, 1, b, c.st); };
   // depthwise stage 1 (sep: dilation 1, dil: dilation 2)
@@ -456,10 +465,11 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
   }
   c.rc |= tc_fwd_on(C, S) ? launch_conv_fwd_tc(db, 15, cst)
           : (S > 1 && tc_sfw_on(C, S)) ? launch_conv_fwd_strided_tc(db, S, cst) : launch_dense_fwd(15, S, db, cst);
-  c.wg_join();
+  c.join(1);
+  c.join(2);
   finalize(c, fs, fc, fr, nf);
   nf = 0;
-  cst = c.wg_stream();
+  cst = c.fork(1);
   // ---- stage 2 (sep_conv second half, conv_15 second conv) reads BN+ReLU of stage 1 on the fly
   for (int v = 0; v < 2; ++v) {
     DwBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = dwP[v];
@@ -500,7 +510,7 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
     fin_add(e, GNAS_CONV15, 1);
   }
   c.rc |= tc_fwd_on(C, 1) ? launch_conv_fwd_tc(db, 15, cst) : launch_dense_fwd(15, 1, db, cst);
-  c.wg_join();
+  c.join(1);
   finalize(c, fs, fc, fr, nf);
 }
 
@@ -688,8 +698,10 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
   const int dwk[4] = {GNAS_SEP15, GNAS_SEP9, GNAS_DIL15, GNAS_DIL9};
   const int dwK[4] = {15, 9, 15, 9}, dwD[4] = {1, 1, 2, 2}, dwP[4] = {7, 4, 14, 8};
   const int tmp0[4] = {TMP_SEP15, TMP_SEP9, TMP_DIL15, TMP_DIL9};
-  // ---- pools + identity skip
+  // ---- pools + identity skip: they only need the coefficients above; their read-modify-write of dX runs on side
+  // stream 2 beside the pointwise / depthwise / conv_15 kernels that do not touch dX (joined before the fused edge kernel)
   {
+    cudaStream_t pst = c.fork(2);
     PoolBwdBatch pb; pb.n = 0; pb.B = B; pb.C = C; pb.mixw = c.mixw;
     for (int i = 0; i < ne; ++i) {
       const int e = edges[i];
@@ -697,7 +709,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
       const OpPlan& mx = E.op[GNAS_MAX_POOL]; const OpPlan& av = E.op[GNAS_AVG_POOL]; const OpPlan& sk = E.op[GNAS_SKIP];
       const bool idskip = sk.on && E.stride == 1;
       if (!mx.on && !av.on && !idskip) continue;
-      if (pb.n > 0 && (pb.S != E.stride || pb.n == kMaxPool)) launch_pool_bwd(pb, c.st);
+      if (pb.n > 0 && (pb.S != E.stride || pb.n == kMaxPool)) launch_pool_bwd(pb, pst);
       pb.S = E.stride;
       PoolBwdJob& j = pb.j[pb.n++];
       j.g = g; j.gbs = gbs; c.src(e, j.x, j.xbs);
@@ -706,7 +718,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
       j.skip_mask = idskip ? c.mask(e) : nullptr;
       j.dx = dsrc[i]; j.dxbs = dsrc_bs[i]; j.Lin = E.Lin; j.Lo = Lo; j.skip_widx = idskip ? c.widx(e, GNAS_SKIP) : -1;
     }
-    launch_pool_bwd(pb, c.st);
+    launch_pool_bwd(pb, pst);
   }
   // The remaining candidates are processed per stride class (edges 0/1 of a reduction cell vs the rest).
   for (int pass = 0; pass < 2; ++pass) {
@@ -718,6 +730,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     if (n2 == 0) continue;
     const int S = c.P.e[es[0]].stride, Lin = c.P.e[es[0]].Lin;
     auto tmp = [&](int i, int which) { return c.scratch + c.P.tmp[is[i]][which]; };
+    cudaStream_t s3 = c.fork(3);      // data gradient of the second conv_15 convolution: independent of the sep / dil chain
     DxBatch xb; xb.n = 0; xb.B = B; xb.Cin = C; xb.pad = 0;
     WgBatch gb; gb.n = 0; gb.B = B; gb.Cout = C;
     auto pw_dx = [&](DxBatch& b) { return tc_pw_on(C) ? launch_conv_dx_tc(b, 1, c.st) : launch_dense_dx(1, 1, b, c.st); };
@@ -757,7 +770,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
           w.Cin = C; w.Lo = Lo; w.Lin = Lin; w.tin = T_RELU;
         }
       }
-      c.rc |= launch_dense_dx(1, S, xb, c.st);
+      if (xb.n) c.rc |= launch_dense_dx(1, S, xb, c.fork(2));
       if (gb.n) c.rc |= launch_pw_wgrad(S, gb, c.wg_stream());
     }
     // -- last pointwise conv of sep (stage 2) and dil: du = W^T dz, dWpw
@@ -823,7 +836,8 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
         w.Cin = C; w.Lo = Lo; w.Lin = Lo; w.tin = T_BN_RELU;
       }
     }
-    c.rc |= tc_dx_on(C, 1, 1) ? launch_conv_dx_tc(xb, 15, c.st) : launch_dense_dx(15, 1, xb, c.st);
+    c.rc |= tc_dx_on(C, 1, 1) ? launch_conv_dx_tc(xb, 15, s3) : launch_dense_dx(15, 1, xb, s3);
+    c.join(3);
     c.rc |= conv_wg(gb, 1);
     // -- inner BN coefficients (w = 1)
     {
@@ -858,6 +872,7 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     c.rc |= pw_dx(xb);
     c.rc |= pw_wg(gb);
     // fused: every depthwise candidate that writes dX of the edge (sep stage 1: du1, dil: du) in one pass over x
+    c.join(2);      // pool / skip gradients have landed in dX
     {
       EdgeBwdBatch eb; eb.n = 0; eb.B = B; eb.C = C;
       for (int i = 0; i < n2; ++i) {
@@ -899,7 +914,9 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
             : (S > 1 && tc_sdx_on(C, S)) ? launch_conv_dx_strided_tc(xb, S, c.st) : launch_dense_dx(15, S, xb, c.st);
     c.rc |= conv_wg(gb, S);
   }
-  c.wg_join();      // the next node reuses the edge temporaries the forked weight-gradient kernels read
+  c.join(1);      // the next node reuses the edge temporaries the forked weight-gradient kernels read
+  c.join(2);
+  c.join(3);
 }
 
 void preprocess_backward(Ctx& c, float* ds0, float* ds1, int need_wgrad) {
@@ -1028,7 +1045,7 @@ extern "C" int gnas_cell_forward(const GnasCellDesc* d, const float* params, flo
   c.d = d; make_plan(d, c.P);
   c.params = params; c.grads = nullptr; c.running = bn_running; c.s0 = s0; c.s1 = s1; c.mixw = mixw;
   c.skip_mask = skip_mask_host; c.out = out; c.ws = ws; c.scratch = nullptr; c.st = (cudaStream_t)stream;
-  c.wside = side_stream(1);
+  c.init_sides(true);
   if (d->training)
     cudaMemsetAsync(ws + c.P.acc, 0, sizeof(double) * (size_t)c.P.nslots * 2 * d->C, c.st);
   pack_forward(c);
@@ -1075,7 +1092,7 @@ extern "C" int gnas_cell_backward(const GnasCellDesc* d, const float* params, fl
   c.params = params; c.grads = grads; c.running = nullptr; c.s0 = s0; c.s1 = s1; c.mixw = mixw;
   c.skip_mask = skip_mask_host; c.out = const_cast<float*>(out); c.ws = const_cast<float*>(ws); c.scratch = scratch;
   c.st = (cudaStream_t)stream;
-  c.wside = side_stream(need_wgrad ? 1 : -1);
+  c.init_sides(true);
   const int C = d->C, B = d->B, Lo = d->L_out;
   const long long obs = (long long)C * Lo;
   // bacc | dmix | coef sit at the head of the scratch: zero the accumulators

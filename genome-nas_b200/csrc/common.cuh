@@ -117,7 +117,7 @@ static inline bool need_prepare(int* table, int want) {
 
 // A second stream per device and purpose for work that is off the critical path of a backward pass (fork / join by
 // events, which a CUDA-graph capture of the caller's stream records as plain dependencies).  `which`: 0 = RHN
-// backward products (GNAS_RHN_SIDE=0 disables), 1 = cell weight gradients (GNAS_WG_SIDE=0 disables).  st == nullptr:
+// backward products (GNAS_RHN_SIDE=0 disables), 1..3 = independent chains of a cell pass (GNAS_WG_SIDE=0 disables).  st == nullptr:
 // not available (emulator, disabled, stream creation failed) -- callers then stay on their own stream.
 #ifdef GNAS_EMUL      // the emulator has one in-order queue: these are never called
 typedef void* cudaEvent_t;

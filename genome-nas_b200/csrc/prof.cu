@@ -42,10 +42,10 @@ SideStream side_stream(int which) {
   (void)which;
   return none;
 #else
-  constexpr int kWhich = 2;
+  constexpr int kWhich = 4;
   static SideStream table[kWhich][kMaxDevices];
   static bool made[kWhich][kMaxDevices] = {{false}};
-  static int enabled[kWhich] = {-1, -1};
+  static int enabled[kWhich] = {-1, -1, -1, -1};
   if (which < 0 || which >= kWhich) return none;
   if (enabled[which] < 0) { const char* e = getenv(which == 0 ? "GNAS_RHN_SIDE" : "GNAS_WG_SIDE"); enabled[which] = e ? atoi(e) : 1; }
   int dev = 0;
