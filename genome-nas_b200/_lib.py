@@ -38,6 +38,7 @@ _SIGS = {
     "gnas_profile_enable": (C.c_int, [C.c_int]),
     "gnas_profile_report": (C.c_int64, [C.c_char_p, C.c_int64]),
     "gnas_profile_event_overhead_ms": (C.c_double, [C.c_int, _P]),
+    "gnas_side_streams": (C.c_int, [C.c_int]),
     "gnas_cell_workspace": (C.c_int, [C.POINTER(CellDesc), _I64P, _I64P]),
     "gnas_cell_forward": (C.c_int, [C.POINTER(CellDesc), _P, _P, _P, _P, _P, _I64P, _P, _P, _P]),
     "gnas_cell_backward": (C.c_int, [C.POINTER(CellDesc), _P, _P, _P, _P, _P, _I64P, _P, _P, _P, _P, _P, _P, _P,
@@ -106,6 +107,11 @@ def kernel_launches():
 
 def profile(enable):
     lib().gnas_profile_enable(1 if enable else 0)
+
+
+def side_streams(on):
+    """Enable / disable the library's side streams (concurrent independent kernel chains); returns the previous setting."""
+    return bool(lib().gnas_side_streams(1 if on else 0))
 
 
 def profile_report():

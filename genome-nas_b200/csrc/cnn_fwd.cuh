@@ -480,22 +480,44 @@ constexpr int kMaxTerms = 40;
 struct MixBatch { int B, C, L, nterms; float* out; long long obs; const float* mixw; MixTerm t[kMaxTerms]; };
 
 // node[b,c,l] = sum_terms w * (z - mean[c]) * rstd[c]      (model_discCNN.py:93,195)
+// Thread = 4 consecutive positions of one row (128-bit loads when every row is 16-byte aligned); the term loop is
+// unrolled so that four independent tensor streams are in flight per thread.
 static __global__ void __launch_bounds__(kThreads) k_mix_fwd(const __grid_constant__ MixBatch P) {
-  const long long total = (long long)P.B * P.C * P.L;
   const int CL = P.C * P.L;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / CL);
-    const int r = (int)(i - (long long)b * CL);
-    const int c = r / P.L;
-    float a = 0.f;
+  const int L4 = (P.L + 3) / 4;                                  // groups of 4 positions per row
+  const long long groups = (long long)P.B * P.C * L4;
+  bool vec = (P.L % 4 == 0) && (P.obs % 4 == 0);
+  for (int t = 0; t < P.nterms; ++t) vec = vec && (P.t[t].bs % 4 == 0);
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (long long)gridDim.x * blockDim.x) {
+    const long long rowi = gi / L4;
+    const int l0 = (int)(gi - rowi * L4) * 4;
+    const int b = (int)(rowi / P.C), c = (int)(rowi - (long long)b * P.C);
+    const int r = c * P.L + l0;
+    const int nv = min(4, P.L - l0);
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
     for (int t = 0; t < P.nterms; ++t) {
       const MixTerm& T = P.t[t];
-      float v = T.z[(long long)b * T.bs + r];
-      if (T.stat) v = (v - T.stat[c]) * T.stat[P.C + c];
-      else if (T.mask) v *= T.mask[i];
-      a = fmaf(P.mixw[T.widx], v, a);
+      const float* zp = T.z + (long long)b * T.bs + r;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec) { const float4 q = *reinterpret_cast<const float4*>(zp); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+      else { for (int e = 0; e < nv; ++e) v[e] = zp[e]; }
+      const float w = P.mixw[T.widx];
+      if (T.stat) {
+        const float rstd = T.stat[P.C + c], mean = T.stat[c];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[e] = fmaf(w, (v[e] - mean) * rstd, a[e]);
+      } else if (T.mask) {
+        const float* mk = T.mask + (long long)b * CL + r;
+        for (int e = 0; e < nv; ++e) a[e] = fmaf(w, v[e] * mk[e], a[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[e] = fmaf(w, v[e], a[e]);
+      }
     }
-    P.out[(long long)b * P.obs + r] = a;
+    float* op = P.out + (long long)b * P.obs + r;
+    if (vec) *reinterpret_cast<float4*>(op) = make_float4(a[0], a[1], a[2], a[3]);
+    else for (int e = 0; e < nv; ++e) op[e] = a[e];
   }
 }
 

@@ -36,6 +36,8 @@ std::string tidy(const char* kernel, const char* where) {
 }
 }  // namespace
 
+static int g_side_on = 1;
+
 SideStream side_stream(int which) {
   SideStream none; none.st = nullptr; none.fork = nullptr; none.join[0] = none.join[1] = nullptr;
 #ifdef GNAS_EMUL
@@ -46,7 +48,7 @@ SideStream side_stream(int which) {
   static SideStream table[kWhich][kMaxDevices];
   static bool made[kWhich][kMaxDevices] = {{false}};
   static int enabled[kWhich] = {-1, -1, -1, -1};
-  if (which < 0 || which >= kWhich) return none;
+  if (which < 0 || which >= kWhich || !g_side_on) return none;
   if (enabled[which] < 0) { const char* e = getenv(which == 0 ? "GNAS_RHN_SIDE" : "GNAS_WG_SIDE"); enabled[which] = e ? atoi(e) : 1; }
   int dev = 0;
   if (!enabled[which] || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return none;
@@ -141,4 +143,10 @@ extern "C" int64_t gnas_profile_report(char* buf, int64_t cap) {
   if ((int64_t)out.size() + 1 > cap) return -1;
   if (buf) { memcpy(buf, out.c_str(), out.size() + 1); }
   return (int64_t)out.size();
+}
+
+extern "C" int gnas_side_streams(int on) {
+  const int prev = gnas::g_side_on;
+  gnas::g_side_on = on ? 1 : 0;
+  return prev;
 }

@@ -43,6 +43,11 @@ int64_t gnas_kernel_launches(void);
  * (returns bytes written, <0 if cap is too small) and clears the records. */
 int gnas_profile_enable(int on);
 int64_t gnas_profile_report(char* buf_host, int64_t cap);
+/* Independent kernel chains of a pass (weight gradients, the conv_15 chain, pool / skip gradients, the off-critical-
+ * path products of the RHN backward) run on library-owned side streams, forked from and joined back into the caller's
+ * stream by events inside every call (a CUDA-graph capture records them as dependencies).  on = 0 serialises
+ * everything on the caller's stream (bench.py does so for its per-kernel timing steps); returns the previous setting. */
+int gnas_side_streams(int on);
 /* median elapsed time (ms) of n empty event pairs on `stream`: the bracketing overhead, measured live */
 double gnas_profile_event_overhead_ms(int n, void* stream);
 
