@@ -623,11 +623,12 @@ void preprocess_forward(Ctx& c) {
     j.z = c.ws + c.P.pre_z[i]; j.zbs = bs; j.acc = d->training ? c.acc(i) : nullptr;
     j.Cin = Cin; j.Lin = Lin; j.Lout = d->L_p; j.tin = T_RELU;
   };
-  if (d->pre0_factorized) {
+  if (d->pre0_factorized) {      // two different kernels on two different inputs: side by side
     job(0, c.s0, d->C_pp, d->L_pp);
-    c.rc |= launch_dense_fwd(1, 2, db, c.st);
+    c.rc |= launch_dense_fwd(1, 2, db, c.fork(2));
     job(1, c.s1, d->C_p, d->L_p);
     c.rc |= launch_dense_fwd(1, 1, db, c.st);
+    c.join(2);
   } else {
     job(0, c.s0, d->C_pp, d->L_pp);
     job(1, c.s1, d->C_p, d->L_p);
@@ -929,8 +930,10 @@ void preprocess_backward(Ctx& c, float* ds0, float* ds1, int need_wgrad) {
     rb.B = B; rb.C = C; rb.L = Lp; rb.nterms = 1; rb.s1_slot = -1;
     rb.g = c.scratch + c.P.dS[i]; rb.gbs = bs; rb.bacc = reinterpret_cast<double*>(c.scratch + c.P.bacc); rb.dmix = c.dmix();
     rb.t[0].z = c.ws + c.P.pre_z[i]; rb.t[0].bs = bs; rb.t[0].mask = nullptr; rb.t[0].slot = i; rb.t[0].widx = -1;
-    GNAS_LAUNCH(k_bwd_reduce, dim3(C, cdiv(B, 8), red_term_chunks(rb.nterms)), dim3(kThreads), 0, c.st, rb);
+    // the two preprocess branches are independent up to the coefficient kernel and again after it: branch 0 on side stream 2
+    GNAS_LAUNCH(k_bwd_reduce, dim3(C, cdiv(B, 8), red_term_chunks(rb.nterms)), dim3(kThreads), 0, i == 0 ? c.fork(2) : c.st, rb);
   }
+  c.join(2);
   {
     CoefBatch cb;
     cb.bacc = reinterpret_cast<const double*>(c.scratch + c.P.bacc); cb.stat = c.ws + c.P.stat; cb.coef = c.scratch + c.P.coef;
@@ -944,23 +947,26 @@ void preprocess_backward(Ctx& c, float* ds0, float* ds1, int need_wgrad) {
   const int Cin[2] = {d->C_pp, d->C_p}, Lin[2] = {d->L_pp, d->L_p};
   const int S[2] = {d->pre0_factorized ? 2 : 1, 1};
   for (int i = 0; i < 2; ++i) {
-    cudaMemsetAsync(dxs[i], 0, sizeof(float) * (size_t)B * Cin[i] * Lin[i], c.st);
+    cudaStream_t bst = i == 0 ? c.fork(2) : c.st;
+    cudaMemsetAsync(dxs[i], 0, sizeof(float) * (size_t)B * Cin[i] * Lin[i], bst);
     DxBatch xb; xb.n = 1; xb.B = B; xb.Cin = Cin[i]; xb.pad = 0;
     DxJob& j = xb.j[0];
     j.g = c.scratch + c.P.dS[i]; j.gbs = bs; j.z = c.ws + c.P.pre_z[i]; j.zbs = bs; j.coef = c.coef(i);
     j.wt = c.params + d->pre_w_off[i]; j.out = dxs[i]; j.obs = (long long)Cin[i] * Lin[i];
     j.xin = xs[i]; j.xibs = j.obs; j.xin_stat = nullptr; j.bacc = nullptr;
     j.Cout = C; j.Lo = Lp; j.Lin = Lin[i]; j.omode = O_RELU_ACC;
-    c.rc |= launch_dense_dx(1, S[i], xb, c.st);
+    c.rc |= launch_dense_dx(1, S[i], xb, bst);
     if (need_wgrad) {
       WgBatch gb; gb.n = 1; gb.B = B; gb.Cout = C;
       WgJob& w = gb.j[0];
       w.g = j.g; w.gbs = bs; w.z = j.z; w.zbs = bs; w.coef = j.coef;
       w.r = xs[i]; w.rbs = j.obs; w.r_stat = nullptr; w.dw = c.grads + d->pre_w_off[i];
       w.Cin = Cin[i]; w.Lo = Lp; w.Lin = Lin[i]; w.tin = T_RELU;
-      c.rc |= launch_pw_wgrad(S[i], gb, c.st);
+      c.rc |= launch_pw_wgrad(S[i], gb, i == 0 ? bst : c.wg_stream());
     }
   }
+  c.join(1);
+  c.join(2);
 }
 
 void pack_backward(Ctx& c) {
