@@ -318,7 +318,7 @@ FAMILIES = [
     ("k_conv_wgrad", "", "conv15_wgrad", "fp32", None), ("k_pw_wgrad", "", "pre_wgrad", "fp32", "pre_wg"),
     ("k_dense_fwd", "KW = 15", "conv15_simt", "fp32", None), ("k_dense_bwd_dx", "KW = 15", "conv15_simt", "fp32", None),
     ("k_dense_fwd", "KW = 1;", "pre_1x1(fwd+dx)", "fp32", "pre_fb"), ("k_dense_bwd_dx", "KW = 1;", "pre_1x1(fwd+dx)", "fp32", "pre_fb"),
-    ("k_dw_fwd", "", "dw_fwd", "hbm", "dw_fwd_b"), ("k_dw_bwd", "", "dw_bwd", "hbm", "dw_bwd_b"),
+    ("k_dw2_fwd", "", "dw_fwd", "hbm", "dw_fwd_b"), ("k_dw2_bwd", "", "dw_bwd", "hbm", "dw_bwd_b"),
     ("k_edge_fwd", "", "dw_fwd", "hbm", "dw_fwd_b"), ("k_edge_bwd", "", "dw_bwd", "hbm", "dw_bwd_b"),
     ("k_pool_fwd", "", "pool_fwd", "hbm", "pool_fwd_b"), ("k_pool_bwd", "", "pool_bwd", "hbm", "pool_bwd_b"),
     ("k_mix_fwd", "", "mix_fwd", "hbm", "mix_fwd_b"), ("k_bwd_reduce", "", "bwd_reduce", "hbm", "bwd_reduce_b"),

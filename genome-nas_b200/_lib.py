@@ -140,6 +140,11 @@ def stream_ptr(t):
     if _device_type != "cuda":
         return C.c_void_p(0)
     import torch
+    # one process per GPU: kernels, per-device kernel attributes and the library's side streams all belong to the
+    # CURRENT device -- a tensor on another device would be launched on the wrong one
+    if t.device.index is not None and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"genome_nas_b200: tensor on {t.device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; call torch.cuda.set_device({t.device.index}) first")
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 

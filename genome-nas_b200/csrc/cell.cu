@@ -471,18 +471,19 @@ void edges_forward(Ctx& c, const int* edges, int ne) {
   nf = 0;
   cst = c.fork(1);
   // ---- stage 2 (sep_conv second half, conv_15 second conv) reads BN+ReLU of stage 1 on the fly
-  for (int v = 0; v < 2; ++v) {
-    DwBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = dwP[v];
-    for (int i = 0; i < ne; ++i) {
-      const int e = edges[i];
-      const OpPlan& O = c.P.e[e].op[dwk[v]];
-      if (!O.on) continue;
-      DwJob& j = wb.j[wb.n++];
-      j.x = c.T(e, dwk[v], 1); j.xbs = obs; j.in_stat = c.stat(O.slot[0]); j.wd = c.W(e, dwk[v], 2);
-      j.u = c.T(e, dwk[v], 2); j.ubs = obs; j.Lin = Lo; j.Lout = Lo; j.tin = T_BN_RELU;
-      if (wb.n == kMaxDw) c.rc |= launch_dw_fwd(dwK[v], 1, 1, wb, c.st);
-    }
-    c.rc |= launch_dw_fwd(dwK[v], 1, 1, wb, c.st);
+  {
+    DwBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = 0;
+    for (int v = 0; v < 2; ++v)
+      for (int i = 0; i < ne; ++i) {
+        const int e = edges[i];
+        const OpPlan& O = c.P.e[e].op[dwk[v]];
+        if (!O.on) continue;
+        DwJob& j = wb.j[wb.n++];
+        j.x = c.T(e, dwk[v], 1); j.xbs = obs; j.in_stat = c.stat(O.slot[0]); j.wd = c.W(e, dwk[v], 2);
+        j.u = c.T(e, dwk[v], 2); j.ubs = obs; j.Lin = Lo; j.Lout = Lo; j.tin = T_BN_RELU; j.K = dwK[v];
+        if (wb.n == kMaxDw) c.rc |= launch_dw2_fwd(wb, c.st);
+      }
+    c.rc |= launch_dw2_fwd(wb, c.st);
   }
   db.pad = 0;
   for (int i = 0; i < ne; ++i) {
@@ -797,27 +798,23 @@ void node_backward(Ctx& c, int node, const float* g, long long gbs, float* const
     }
     c.rc |= pw_dx(xb);
     c.rc |= pw_wg(gb);
-    // -- depthwise: sep stage 2 (-> dyh1 + inner BN sums); the dil depthwise convs (-> dX) join the fused edge kernel below
-    for (int v = 0; v < 2; ++v) {
-      const bool sep = true;
-      DwBwdBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = dwP[v];
-      for (int i = 0; i < n2; ++i) {
-        const int e = es[i];
-        const OpPlan& O = c.P.e[e].op[dwk[v]];
-        if (!O.on) continue;
-        DwBwdJob& j = wb.j[wb.n++];
-        j.du = tmp(i, tmp0[v]); j.dubs = obs;
-        if (sep) {
+    // -- depthwise: sep stage 2 (-> dyh1 + inner BN sums), both kernel sizes in one launch; the dil depthwise convs
+    // (-> dX) join the fused edge kernel below
+    {
+      DwBwdBatch wb; wb.n = 0; wb.B = B; wb.C = C; wb.pad = 0;
+      for (int v = 0; v < 2; ++v)
+        for (int i = 0; i < n2; ++i) {
+          const int e = es[i];
+          const OpPlan& O = c.P.e[e].op[dwk[v]];
+          if (!O.on) continue;
+          DwBwdJob& j = wb.j[wb.n++];
+          j.du = tmp(i, tmp0[v]); j.dubs = obs;
           j.x = c.T(e, dwk[v], 1); j.xbs = obs; j.in_stat = c.stat(O.slot[0]); j.wd = c.W(e, dwk[v], 2);
           j.out = tmp(i, tmp0[v] + 1); j.obs = obs; j.bacc = c.bacc(O.slot[0]);
           j.dwd = need_wgrad ? c.dW(e, dwk[v], 2) : nullptr; j.Lin = Lo; j.Lo = Lo; j.tin = T_BN_RELU; j.omode = O_BNRELU_STORE;
-        } else {
-          c.src(e, j.x, j.xbs); j.in_stat = nullptr; j.wd = c.W(e, dwk[v], 0);
-          j.out = dsrc[is[i]]; j.obs = dsrc_bs[is[i]]; j.bacc = nullptr;
-          j.dwd = need_wgrad ? c.dW(e, dwk[v], 0) : nullptr; j.Lin = Lin; j.Lo = Lo; j.tin = T_RELU; j.omode = O_RELU_ACC;
+          j.K = dwK[v];
         }
-      }
-      c.rc |= launch_dw_bwd(dwK[v], dwD[v], sep ? 1 : S, wb, c.st);
+      c.rc |= launch_dw2_bwd(wb, c.st);
     }
     // -- conv_15 second conv: dyh1 + inner BN sums, dW2
     xb.pad = 7;

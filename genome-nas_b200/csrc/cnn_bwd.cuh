@@ -533,6 +533,7 @@ struct DwBwdJob {
   double* bacc;                      // (sum v, sum v*z1)[C] for O_BNRELU_STORE
   float* dwd;                        // [C][K] atomics, or null
   int Lin, Lo, tin, omode;
+  int K;                             // 15 or 9 (k_dw2_bwd picks the instance per job)
 };
 struct DwBwdBatch { int n, B, C, pad, RPW, nseg; DwBwdJob j[kMaxDw]; };
 
@@ -553,7 +554,7 @@ struct DwBwdGeom {
 // of strided edges): every lane produces 4 consecutive positions from register windows (128-bit shared loads, static
 // tap indices).  The staging loops have compile-time bounds: all global loads of a tile are in flight at once.
 template <int K, int D, int S>
-__global__ void __launch_bounds__(kThreads, 4) k_dw_bwd(const __grid_constant__ DwBwdBatch P) {
+__device__ __forceinline__ void dw_bwd_body(const DwBwdBatch& P) {
   using G = DwBwdGeom<K, D, S>;
   constexpr int PADC = G::PADC, OFF = G::OFF, SEG = G::SEG, WX = G::WX, WD = G::WD;
   static_assert(SEG % S == 0 && SEG % 4 == 0, "segment must be a multiple of the stride and of 4");
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dw_bwd(const __grid_constant__ 
     float xv_[(WX + 31) / 32], dv_[(WD + 31) / 32];
 #pragma unroll
     for (int q = 0; q < (WX + 31) / 32; ++q) {
-      const int pos = m0 - P.pad + lane + 32 * q;
+      const int pos = m0 - PADC + lane + 32 * q;
       xv_[q] = (pos >= 0 && pos < J.Lin) ? xg[pos] : 0.f;
     }
 #pragma unroll
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dw_bwd(const __grid_constant__ 
     }
 #pragma unroll
     for (int q = 0; q < (WX + 31) / 32; ++q) {
-      const int p = lane + 32 * q, pos = m0 - P.pad + p;
+      const int p = lane + 32 * q, pos = m0 - PADC + p;
       if (p < WX) xrow[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xv_[q], J.tin, mean, rstd) : 0.f;
     }
 #pragma unroll
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dw_bwd(const __grid_constant__ 
       _Pragma("unroll 4")
       for (int ml = lane; ml < nm; ml += 32) {
         const int m = m0 + ml;
-        if (J.omode == O_RELU_ACC) { if (xrow[ml + P.pad] > 0.f) orow[m] += arow[ml]; }
+        if (J.omode == O_RELU_ACC) { if (xrow[ml + PADC] > 0.f) orow[m] += arow[ml]; }
         else { const float xv = xg[m]; const float v = xv > mean ? arow[ml] : 0.f; orow[m] = v; s += v; qq = fmaf(v, xv, qq); }
       }
       // dwd[c,t] += sum_l du[l] * T(x)[l + t*D - pad]   (xrow index = (l - l0) + t*D)
@@ -663,7 +664,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dw_bwd(const __grid_constant__ 
         float a = 0.f;
 #pragma unroll
         for (int t = 0; t < K; ++t) {
-          const int num = m + P.pad - t * D;
+          const int num = m + PADC - t * D;
           if (num >= 0 && num % S == 0) a = fmaf(w[t], drow[num / S - l0 + OFF], a);
         }
         const float xv = xg[m];
@@ -704,6 +705,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_dw_bwd(const __grid_constant__ 
       else atomicAdd(&J.bacc[(v - K) * P.C + c], (double)t);
     }
   }
+}
+
+// second depthwise convolution of sep_conv_15 and sep_conv_9 (stride 1, dilation 1) in one launch: the kernel size is
+// a per-job switch between the two instances (two dependent launches per node before)
+static __global__ void __launch_bounds__(kThreads, 4) k_dw2_bwd(const __grid_constant__ DwBwdBatch P) {
+  if (P.j[blockIdx.z].K == 15) dw_bwd_body<15, 1, 1>(P); else dw_bwd_body<9, 1, 1>(P);
 }
 
 // ------------------------------------------------------------------ fused edge backward (north star (1): fused backward)

@@ -204,6 +204,7 @@ struct DwJob {
   const float* wd;                 // [C][K]
   float* u; long long ubs;         // output [B][C][Lout]
   int Lin, Lout, tin;
+  int K;                           // 15 or 9 (k_dw2_fwd picks the instance per job)
 };
 constexpr int kMaxDw = 16;
 struct DwBatch { int n, B, C, pad, nseg; DwJob j[kMaxDw]; };
@@ -217,9 +218,9 @@ struct DwFwdGeom {
 
 // u[b,c,l] = sum_t wd[c,t] * T(x)[b,c,l*S+t*D-pad];  CTA: batch row b, 8 channels (one per warp), one output segment
 template <int K, int D, int S>
-__global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwBatch P) {
+__device__ __forceinline__ void dw_fwd_body(const DwBatch& P) {
   using G = DwFwdGeom<K, D, S>;
-  constexpr int SEGO = G::SEGO, WP = G::WP;
+  constexpr int SEGO = G::SEGO, WP = G::WP, PADC = (K - 1) * D / 2;
   const DwJob& J = P.j[blockIdx.z];
   const int b = blockIdx.y / P.nseg, seg = blockIdx.y - b * P.nseg;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -238,12 +239,12 @@ __global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwB
     float xv[(WP + 31) / 32];
 #pragma unroll
     for (int q = 0; q < (WP + 31) / 32; ++q) {
-      const int pos = l0 * S - P.pad + lane + 32 * q;
+      const int pos = l0 * S - PADC + lane + 32 * q;
       xv[q] = (pos >= 0 && pos < J.Lin) ? xr[pos] : 0.f;
     }
 #pragma unroll
     for (int q = 0; q < (WP + 31) / 32; ++q) {
-      const int p = lane + 32 * q, pos = l0 * S - P.pad + p;
+      const int p = lane + 32 * q, pos = l0 * S - PADC + p;
       if (p < WP) row[p] = (pos >= 0 && pos < J.Lin) ? apply_tin(xv[q], J.tin, mean, rstd) : 0.f;
     }
   }
@@ -274,6 +275,11 @@ __global__ void __launch_bounds__(kThreads) k_dw_fwd(const __grid_constant__ DwB
     _Pragma("unroll 4")
     for (int l = l0 + lane; l < l1; l += 32) ur[l] = orow[l - l0];
   }
+}
+
+// second depthwise convolution of sep_conv_15 and sep_conv_9 in one launch (per-job kernel size)
+static __global__ void __launch_bounds__(kThreads) k_dw2_fwd(const __grid_constant__ DwBatch P) {
+  if (P.j[blockIdx.z].K == 15) dw_fwd_body<15, 1, 1>(P); else dw_fwd_body<9, 1, 1>(P);
 }
 
 // ------------------------------------------------------------------ fused edge forward (north star (1))

@@ -80,28 +80,6 @@ static int launch_dense_fwd(int KW, int S, DenseBatch& b, cudaStream_t st) {
   return 0;
 }
 
-// ------------------------------------------------------------------ depthwise forward
-template <int K, int D, int S>
-static void launch_dw_fwd_t(DwBatch& b, cudaStream_t st) {
-  int lout = 1;
-  for (int i = 0; i < b.n; ++i) lout = b.j[i].Lout > lout ? b.j[i].Lout : lout;
-  b.nseg = cdiv(lout, DwFwdGeom<K, D, S>::SEGO);
-  dim3 grid(cdiv(b.C, 8), b.B * b.nseg, b.n);
-  GNAS_LAUNCH((k_dw_fwd<K, D, S>), grid, dim3(kThreads), 0, st, b);
-}
-static int launch_dw_fwd(int K, int D, int S, DwBatch& b, cudaStream_t st) {
-  if (b.n == 0) return 0;
-#define GNAS_DW_CASE(k, d, s) if (K == k && D == d && S == s) launch_dw_fwd_t<k, d, s>(b, st); else
-  GNAS_DW_CASE(15, 1, 1) GNAS_DW_CASE(15, 1, 2) GNAS_DW_CASE(15, 1, 3)
-  GNAS_DW_CASE(9, 1, 1) GNAS_DW_CASE(9, 1, 2) GNAS_DW_CASE(9, 1, 3)
-  GNAS_DW_CASE(15, 2, 1) GNAS_DW_CASE(15, 2, 2) GNAS_DW_CASE(15, 2, 3)
-  GNAS_DW_CASE(9, 2, 1) GNAS_DW_CASE(9, 2, 2) GNAS_DW_CASE(9, 2, 3)
-  { set_error("dw_fwd: unsupported (K, D, S)"); return GNAS_ERR_UNSUPPORTED; }
-#undef GNAS_DW_CASE
-  b.n = 0;
-  return 0;
-}
-
 // ------------------------------------------------------------------ transposed dense (dx)
 template <int KW, int S, int TM>
 static void launch_dense_dx_t(DxBatch& b, int maxLin, cudaStream_t st) {
@@ -239,32 +217,31 @@ static int launch_conv_wgrad(int KW, int S, int pad, WgBatch& b, cudaStream_t st
   return 0;
 }
 
-// ------------------------------------------------------------------ depthwise backward
-template <int K, int D, int S>
-static void launch_dw_bwd_t(DwBwdBatch& b, cudaStream_t st) {
-  using G = DwBwdGeom<K, D, S>;
+// ------------------------------------------------------------------ depthwise (second stage of sep_conv)
+// second depthwise convolution of the sep_conv candidates: K = 15 and K = 9 jobs in one launch
+static int launch_dw2_fwd(DwBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  int lout = 1;
+  for (int i = 0; i < b.n; ++i) lout = b.j[i].Lout > lout ? b.j[i].Lout : lout;
+  b.nseg = cdiv(lout, DwFwdGeom<15, 1, 1>::SEGO);
+  dim3 grid(cdiv(b.C, 8), b.B * b.nseg, b.n);
+  GNAS_LAUNCH(k_dw2_fwd, grid, dim3(kThreads), 0, st, b);
+  b.n = 0;
+  return 0;
+}
+static int launch_dw2_bwd(DwBwdBatch& b, cudaStream_t st) {
+  if (b.n == 0) return 0;
+  using G = DwBwdGeom<15, 1, 1>;
   int lin = 1;
   for (int i = 0; i < b.n; ++i) lin = b.j[i].Lin > lin ? b.j[i].Lin : lin;
   b.nseg = cdiv(lin, G::SEG);
   const size_t smem = sizeof(float) * 8 * (size_t)(G::WX + G::WD + G::SEG);
-  GNAS_PREP_SMEM((k_dw_bwd<K, D, S>), smem);
-  // rows per warp: reduce the per-row reduction/atomic overhead only when the grid is far larger than the machine
+  GNAS_PREP_SMEM(k_dw2_bwd, smem);
   int rpw = (b.C * cdiv(b.B, 8) * b.n * b.nseg) / (16 * 148);
   rpw = rpw < 1 ? 1 : (rpw > 2 ? 2 : rpw);
   b.RPW = rpw;
   dim3 grid(b.C, cdiv(b.B, 8 * rpw) * b.nseg, b.n);
-  GNAS_LAUNCH((k_dw_bwd<K, D, S>), grid, dim3(kThreads), smem, st, b);
-}
-static int launch_dw_bwd(int K, int D, int S, DwBwdBatch& b, cudaStream_t st) {
-  if (b.n == 0) return 0;
-  if (b.pad != (K - 1) * D / 2) { set_error("dw_bwd: padding must be (K-1)*D/2"); return GNAS_ERR_UNSUPPORTED; }
-#define GNAS_DW_CASE(k, d, s) if (K == k && D == d && S == s) launch_dw_bwd_t<k, d, s>(b, st); else
-  GNAS_DW_CASE(15, 1, 1) GNAS_DW_CASE(15, 1, 2) GNAS_DW_CASE(15, 1, 3)
-  GNAS_DW_CASE(9, 1, 1) GNAS_DW_CASE(9, 1, 2) GNAS_DW_CASE(9, 1, 3)
-  GNAS_DW_CASE(15, 2, 1) GNAS_DW_CASE(15, 2, 2) GNAS_DW_CASE(15, 2, 3)
-  GNAS_DW_CASE(9, 2, 1) GNAS_DW_CASE(9, 2, 2) GNAS_DW_CASE(9, 2, 3)
-  { set_error("dw_bwd: unsupported (K, D, S)"); return GNAS_ERR_UNSUPPORTED; }
-#undef GNAS_DW_CASE
+  GNAS_LAUNCH(k_dw2_bwd, grid, dim3(kThreads), smem, st, b);
   b.n = 0;
   return 0;
 }

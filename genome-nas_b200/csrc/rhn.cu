@@ -572,16 +572,20 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem(const __grid_c
     const bool r0 = lane < B, r1 = lane + 32 < B;
     const float d0 = r0 ? dsr[lane] : 0.f, d1 = r1 ? dsr[lane + 32] : 0.f;
     const float h0 = r0 ? shr[lane] : 0.f, h1 = r1 ? shr[lane + 32] : 0.f;
-    const float S1 = warp_sum(d0 + d1) / (float)B;
-    const float S2 = warp_sum(d0 * h0 + d1 * h1) / (float)B;
-    const float dr0 = rstd * (d0 - S1 - h0 * S2), dr1 = rstd * (d1 - S1 - h1 * S2);
-    float pk[4], q = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { const int ix = P.tb.pidx[p][k]; pk[k] = ix >= 0 ? P.probs[ix] : 0.f; q += pk[k]; }
     float* cp = P.CHT + (((size_t)P.t * 36 + p) * 2) * HB + row;
     float* hp = cp + HB;
     const float* sjr = P.ST + ((size_t)P.t * 9 + j) * HB + row;
     float* dsj = P.dsT + (size_t)j * HB + row;
+    // every operand is fetched before the two batch reductions: one exposure to the load latency instead of two
+    const float cv0 = r0 ? cp[lane] : 0.f, cv1 = r1 ? cp[lane + 32] : 0.f;
+    const float hv0 = r0 ? hp[lane] : 0.f, hv1 = r1 ? hp[lane + 32] : 0.f;
+    const float sj0 = r0 ? sjr[lane] : 0.f, sj1 = r1 ? sjr[lane + 32] : 0.f;
+    float pk[4], q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int ix = P.tb.pidx[p][k]; pk[k] = ix >= 0 ? P.probs[ix] : 0.f; q += pk[k]; }
+    const float S1 = warp_sum(d0 + d1) / (float)B;
+    const float S2 = warp_sum(d0 * h0 + d1 * h1) / (float)B;
+    const float dr0 = rstd * (d0 - S1 - h0 * S2), dr1 = rstd * (d1 - S1 - h1 * S2);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int m = lane + 32 * half;
@@ -589,7 +593,7 @@ static __global__ void __launch_bounds__(kThreads) k_rhn_bwd_elem(const __grid_c
         float dc = 0.f, dh = 0.f;
         if (m < B) {
           const float dr = half ? dr1 : dr0;
-          const float c = cp[m], h = hp[m], sj = sjr[m];
+          const float c = half ? cv1 : cv0, h = half ? hv1 : hv0, sj = half ? sj1 : sj0;
           const float g = sigmoidf_(c);
           float F = 0.f, Fp = 0.f;
 #pragma unroll

@@ -46,9 +46,17 @@ def main():
         errs += [relerr(p.grad, Q["cell_ops.0." + n].grad) for n, p in m.named_parameters()]
         worst = max(worst, max(errs))
         assert max(errs) < 5e-5, (B, C, L, S, max(errs))
+    # the point of this case: the CUDA-core kernels really ran (GNAS_TC=0), no tensor-core kernel did
     from genome_nas_b200 import _lib
-    names = " ".join(_lib.profile_report().keys()) if hasattr(_lib, "profile_report") else ""
-    print(f"simt path ok: worst rel err {worst:.2e} {names[:0]}")
+    _lib.profile(True)
+    m.zero_grad()
+    y = m(x.detach().requires_grad_(True), w.detach().requires_grad_(True))
+    y.sum().backward()
+    names = list(_lib.profile_report().keys())
+    _lib.profile(False)
+    assert any(n.startswith("k_dense_fwd") for n in names) and any(n.startswith("k_dense_bwd_dx") for n in names), names
+    assert not any("_tc" in n for n in names), names
+    print(f"simt path ok: worst rel err {worst:.2e}; {len(names)} distinct kernels, none on tensor cores")
 
 
 if __name__ == "__main__":
