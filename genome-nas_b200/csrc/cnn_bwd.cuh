@@ -48,7 +48,7 @@ static __global__ void __launch_bounds__(kThreads) k_bwd_reduce(const __grid_con
 #pragma unroll
   for (int k = 0; k < kRedTerms; ++k) s2[k] = 0.f;
   if (ok && P.nterms > 0) {
-    _Pragma("unroll 4")
+    _Pragma("unroll 2")
     for (int l = lane; l < P.L; l += 32) {
       const float gl = gr[l];
       s1 += gl;

@@ -341,3 +341,43 @@ def test_infer_matches_oracle_eval_mode(backend):
         assert relerr(torch.from_numpy(p), lo) < 1e-5
         tot += float(F.binary_cross_entropy(lo, y.double()))
     assert abs(float(avg) - tot / 2) < 1e-5 * (tot / 2)
+
+
+@pytest.mark.gpu
+def test_side_streams_do_not_change_results(monkeypatch):
+    """Independent kernel chains of a pass overlap on the library's side streams (fork / join by events inside every C
+    call).  A missing dependency would show as run-to-run garbage: at full size (where the kernels are long enough to
+    overlap for real) two overlapped passes and one serialised pass must agree -- logits to 1e-6 (BN statistics are
+    summed in double), gradients up to the order of the float atomics."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from genome_nas_b200 import _lib
+    _lib._use_library_for_tests(None, "cuda")
+    g = load("full")
+    cfg = g["cfg"]
+    dev = torch.device("cuda:0")
+    m, _ = build(g, dev)
+    xt, yt = O.synthetic_batch(g["B"], cfg.seq_len, cfg.num_classes, 0)
+    xt, yt = xt.to(dev), yt.to(dev)
+    runs = []
+    for side in (True, True, False):
+        prev = _lib.side_streams(side)
+        try:
+            masks = [g["xm"], g["hm"]]
+            monkeypatch.setattr(R, "mask2d", lambda B, D, keep, d: masks.pop(0).to(d))
+            for p in m.parameters():
+                p.grad = None
+            logits, hidden, rnn_hs, _ = m(xt, m.init_hidden(g["B"]), return_h=True)
+            loss = G.bce_loss(logits, yt) + G.tar_loss(rnn_hs[-1], O.Hyper().beta)
+            loss.backward()
+            torch.cuda.synchronize()
+            runs.append((logits.detach().clone(), [p.grad.detach().clone() for p in m.parameters()]))
+        finally:
+            _lib.side_streams(prev)
+        # undo the running-statistics side effect so that every run starts from the same state (not needed for the
+        # training-mode arithmetic, kept for clarity)
+    base_logits, base_grads = runs[-1]
+    for logits, grads in runs[:-1]:
+        assert relerr(logits, base_logits) < 1e-6
+        worst = max(relerr(a, b) for a, b in zip(grads, base_grads) if float(b.abs().max()) > 0)
+        assert worst < 1e-4, worst
