@@ -806,14 +806,27 @@ __device__ __forceinline__ void edge_bwd_cand(const float* dg, const float* wdp,
         }
       }
     } else {
-      _Pragma("unroll 4")
+      // polyphase: position m receives the taps t with (m + pad - t D) % S == 0, i.e. t = t0, t0 + STEP, ... where
+      // t0 < STEP = S / gcd(D, S) solves the congruence (none for D = S = 2 at odd m + pad): K / STEP multiply-adds per
+      // position instead of K divisibility tests
+      _Pragma("unroll 2")
       for (int ml = lane; ml < nm; ml += 32) {
         const int m = m0 + ml;
+        constexpr int STEP = (D % S == 0) ? 1 : S;      // S / gcd(D, S) for D in {1, 2}, S in {2, 3}
+        const int r = (m + PADC) % S;
+        int t0 = -1;
+#pragma unroll
+        for (int c = STEP - 1; c >= 0; --c) if ((r + S * D - c * D) % S == 0) t0 = c;
         float a = arow[ml];
 #pragma unroll
-        for (int t = 0; t < K; ++t) {
-          const int num = m + PADC - t * D;
-          if (num >= 0 && num % S == 0) a = fmaf(w[t], drow[num / S - l0 + OFF], a);
+        for (int c = 0; c < STEP; ++c) {
+          if (t0 != c) continue;            // static tap indices per residue: w[] stays in registers
+#pragma unroll
+          for (int u = 0; u < (K + STEP - 1) / STEP; ++u) {
+            const int t = c + u * STEP;
+            const int num = m + PADC - t * D;
+            if (t < K && num >= 0) a = fmaf(w[t < K ? t : 0], drow[num / S - l0 + OFF], a);
+          }
         }
         arow[ml] = a;
       }
