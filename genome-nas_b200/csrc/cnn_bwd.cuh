@@ -47,7 +47,26 @@ static __global__ void __launch_bounds__(kThreads) k_bwd_reduce(const __grid_con
   float s1 = 0.f, s2[kRedTerms];
 #pragma unroll
   for (int k = 0; k < kRedTerms; ++k) s2[k] = 0.f;
-  if (ok && P.nterms > 0) {
+  // rows that are 16-byte aligned (L % 4 == 0 and every batch stride a multiple of 4): 128-bit loads, 4 positions per lane
+  bool vec = (P.L % 4 == 0) && (P.gbs % 4 == 0) && (reinterpret_cast<uintptr_t>(P.g) & 15) == 0;
+#pragma unroll
+  for (int k = 0; k < kRedTerms; ++k) {
+    const RedTerm& T = P.t[k < nt ? t0 + k : (t0 < P.nterms ? t0 : 0)];
+    vec = vec && (T.bs % 4 == 0) && T.mask == nullptr && (reinterpret_cast<uintptr_t>(T.z) & 15) == 0;
+  }
+  if (ok && P.nterms > 0 && vec) {
+    _Pragma("unroll 2")
+    for (int l = 4 * lane; l < P.L; l += 128) {
+      const float4 g4 = *reinterpret_cast<const float4*>(gr + l);
+      s1 += (g4.x + g4.y) + (g4.z + g4.w);
+#pragma unroll
+      for (int k = 0; k < kRedTerms; ++k) {
+        const float4 z4 = *reinterpret_cast<const float4*>(zr[k] + l);
+        s2[k] = fmaf(g4.x, z4.x, s2[k]); s2[k] = fmaf(g4.y, z4.y, s2[k]);
+        s2[k] = fmaf(g4.z, z4.z, s2[k]); s2[k] = fmaf(g4.w, z4.w, s2[k]);
+      }
+    }
+  } else if (ok && P.nterms > 0) {
     _Pragma("unroll 2")
     for (int l = lane; l < P.L; l += 32) {
       const float gl = gr[l];
