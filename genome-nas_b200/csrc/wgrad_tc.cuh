@@ -214,6 +214,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_pw_wgrad_tc(const __grid_cons
   }
 }
 
+// Batch rows per CTA of a weight-gradient launch.  One CTA owns a whole SM (its operand stages fill the shared
+// memory), so a launch costs ceil(CTAs / SMs) rounds of (rows * stages-per-row + fixed) stages: pick the row count
+// that minimises it instead of a fixed chain length (e.g. 243 CTAs = one full round + one round at 64 %).
+static inline int wgrad_rows_per_cta(int B, int ctas_per_row_split, int spr, int fixed_stages, int max_stages) {
+  static int auto_on = -1;
+  if (auto_on < 0) { const char* e = getenv("GNAS_WG_AUTO"); auto_on = e ? atoi(e) : 1; }
+  if (!auto_on) return 0;
+  int best = 1; long long best_cost = -1;
+  for (int rows = 1; rows <= B; ++rows) {
+    if (rows > 1 && rows * spr > max_stages) break;
+    const long long grid = (long long)cdiv(B, rows) * ctas_per_row_split;
+    const long long cost = cdivll(grid, 148) * ((long long)rows * spr + fixed_stages);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rows; }
+  }
+  return best;
+}
+
 template <int C>
 static void launch_pw_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* name) {
   static int prepared[kMaxDevices] = {0};
@@ -222,6 +239,11 @@ static void launch_pw_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* name
   int ksplit = cdiv(2 * 148, groups);
   ksplit = ksplit > b.B ? b.B : (ksplit < 1 ? 1 : ksplit);
   b.rows_per_cta = cdiv(b.B, ksplit);
+  {
+    const int spr = (b.j[0].Lo + 31) / 32;                   // 32-position stages per batch row
+    const int r = wgrad_rows_per_cta(b.B, groups, spr, 4, 96);      // bounded chains: the tensor core truncates on accumulate
+    if (r > 0) b.rows_per_cta = r;
+  }
   prof_before(name, "", st);
   k_pw_wgrad_tc<C><<<dim3(cdiv(b.B, b.rows_per_cta), groups), dim3(kTcThreads), kPwSmem, st>>>(b);
   prof_after(st);
@@ -510,6 +532,10 @@ static void launch_conv_wgrad_tc_t(WgTcBatch& b, cudaStream_t st, const char* na
   if (chain < 0) { const char* e = getenv("GNAS_WG_CHAIN"); chain = e ? atoi(e) : 10; }
   int rows = chain / spr;                    // ~10 stages (= 40 k-steps) per accumulation chain
   rows = rows < 1 ? 1 : rows;
+  if (!getenv("GNAS_WG_CHAIN")) {
+    const int r = wgrad_rows_per_cta(b.B, b.n * Cfg::NZ, spr, 4, 40);      // chains beyond ~40 stages lose to the truncation bias / parallelism
+    if (r > 0) rows = r;
+  }
   b.rows_per_cta = rows;
   prof_before(name, "", st);
   k_conv_wgrad_tc<C><<<dim3(cdiv(b.B, rows), b.n, Cfg::NZ), dim3(kTcThreads), Cfg::smem, st>>>(b);
