@@ -1,12 +1,9 @@
 #!/bin/bash
-# scratch A/B template for one GPU call: parity tests, then the bench (edit the environment switches per experiment)
+# scratch A/B template for one GPU call (edit the environment switches per experiment)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
-for k in 1 2; do
-timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "rc=$?"; tail -1 gpurun_out/bench.log | cut -c60-190
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1])
-print({k:(round(v['ms_per_step'],3), v['launches_per_step']) for k,v in d['families'].items() if 'mix' in k or 'reduce' in k})
-PY
+for cfg in "1 1" "0 0" "1 1" "0 0"; do
+set -- $cfg
+GNAS_SIDE_PRIO=$1 GNAS_CAPTURE_PRIO=$2 timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-gpu-eager-baseline > gpurun_out/bench_ab.log 2> gpurun_out/bench.err; echo "prio=$1 cap=$2 rc=$?"; tail -1 gpurun_out/bench_ab.log | cut -c60-190; tail -2 gpurun_out/bench.err
 done
+GNAS_SIDE_PRIO=1 GNAS_CAPTURE_PRIO=1 python tools/timeline_step.py 2>&1 | tail -6
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
