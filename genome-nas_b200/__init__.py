@@ -8,7 +8,7 @@ from . import _lib  # noqa: F401
 from .cnn import CNN_Cell_search, MixedOp  # noqa: F401
 from .operations import OPS, PRIMITIVES_cnn, PRIMITIVES_rnn  # noqa: F401
 from .rnn import DARTSCellSearch  # noqa: F401
-from .model import Genotype, RNNModel, RNNModelSearch  # noqa: F401
+from .model import Genotype, RNNModel, RNNModelSearch, encode_onehot, expand_onehot  # noqa: F401
 from .architect import Architect  # noqa: F401
 from .train import Hyper, SearchStep, infer, train  # noqa: F401
 from .head import bce_loss, tar_loss  # noqa: F401

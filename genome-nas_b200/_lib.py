@@ -46,6 +46,7 @@ _SIGS = {
     "gnas_stem_workspace": (C.c_int, [C.c_int, C.c_int, C.c_int, _I64P, _I64P]),
     "gnas_stem_forward": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnas_stem_backward": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gnas_onehot_expand": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "gnas_rhn_workspace": (C.c_int, [C.POINTER(RhnDesc), _I64P, _I64P]),
     "gnas_rhn_forward": (C.c_int, [C.POINTER(RhnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gnas_rhn_backward": (C.c_int, [C.POINTER(RhnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,

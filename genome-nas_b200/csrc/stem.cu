@@ -96,3 +96,26 @@ extern "C" int gnas_stem_backward(int B, int C0, int L, const float* x, const fl
   if (rc) return rc;
   return check_launch("gnas_stem_backward");
 }
+
+// ---- on-device data path: one byte per base instead of the fp32 one-hot [B][4][L] (16x fewer bytes over PCIe).
+// codes[b][l] in {0, 1, 2, 3} = the hot channel, anything else (e.g. 255 for N) = all-zero column.
+// Restates what the reference's loader materialises on the host (data_preprocessing_TF.py:90-149).
+namespace gnas {
+static __global__ void __launch_bounds__(256) k_onehot_expand(const unsigned char* __restrict__ codes, float* __restrict__ x,
+                                                              long long B, long long L) {
+  const long long total = B * L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / L, l = i - b * L;
+    const int c = codes[i];
+    float* xb = x + b * 4 * L + l;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xb[k * L] = c == k ? 1.f : 0.f;
+  }
+}
+}  // namespace gnas
+
+extern "C" int gnas_onehot_expand(const uint8_t* codes, int64_t B, int64_t L, float* x, void* stream) {
+  if (!codes || !x || B < 1 || L < 1) { set_error("onehot_expand: bad argument"); return GNAS_ERR_ARG; }
+  GNAS_LAUNCH(k_onehot_expand, dim3(ew_blocks(B * L)), dim3(256), 0, (cudaStream_t)stream, codes, x, (long long)B, (long long)L);
+  return check_launch("gnas_onehot_expand");
+}

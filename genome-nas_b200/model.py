@@ -28,6 +28,22 @@ from collections import namedtuple
 Genotype = namedtuple('Genotype', 'normal normal_concat reduce reduce_concat rnn rnn_concat')   # genotypes.py:11
 
 
+def encode_onehot(x):
+    """Host-side: fp32 one-hot [B, 4, L] -> uint8 base codes [B, L] (0..3 = hot channel, 255 = all-zero column)."""
+    hot = x.max(dim=1)
+    return torch.where(hot.values > 0, hot.indices, torch.full_like(hot.indices, 255)).to(torch.uint8).contiguous()
+
+
+def expand_onehot(codes):
+    """Device-side inverse of `encode_onehot`: uint8 codes [B, L] -> fp32 one-hot [B, 4, L] (gnas_onehot_expand)."""
+    codes = _lib.require(codes.contiguous(), "base codes", torch.uint8)
+    B, L = codes.shape
+    x = torch.empty(B, 4, L, dtype=torch.float32, device=codes.device)
+    _lib.check(_lib.lib().gnas_onehot_expand(_lib.ptr(codes), B, L, _lib.ptr(x), _lib.stream_ptr(codes)), "onehot_expand")
+    _lib.LAUNCHES += 1
+    return x
+
+
 class _StemFunction(torch.autograd.Function):
     """Conv1d(4, C0, 13, pad 6) + BatchNorm1d(C0) affine (model_discCNN.py:350-353)."""
 
@@ -160,6 +176,8 @@ class RNNModel(nn.Module):
 
     def forward(self, input, hidden, return_h=False):
         region_of(self)
+        if input.dtype == torch.uint8:          # compact data path: base codes [B, L], expanded on the device
+            input = expand_onehot(input)
         s0 = s1 = _StemFunction.apply(self.stem, input, self.stem[0].weight)
         w_normal = w_reduce = None
         for cell in self.cells:

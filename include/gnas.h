@@ -107,6 +107,11 @@ int gnas_stem_backward(int B, int C0, int L, const float* x, const float* w, con
                        const float* dout, const float* ws, float* scratch, float* dw,
                        float* dgamma, float* dbeta, void* stream);
 
+/* ---- compact input: one byte per base (0..3 = hot channel, anything else = all-zero column, e.g. N) expanded on the
+ * device into the fp32 one-hot [B][4][L] the stem reads -- 16x fewer host->device bytes than the tensor the reference's
+ * loader builds on the host (generalNAS_tools/data_preprocessing_TF.py:90-149). */
+int gnas_onehot_expand(const uint8_t* codes, int64_t B, int64_t L, float* x, void* stream);
+
 /* ---- recurrent highway layer of the search cell: darts_tools/model_discCNN.py:226-268
  * (DARTSCell.forward, _compute_init_state) + model_search.py:54-97 (DARTSCellSearch.cell). */
 typedef struct {

@@ -64,6 +64,35 @@ def test_mixedop_shapes(backend, B, C, L, stride, switch):
         assert relerr(p.grad, Q["cell_ops.0." + n].grad) < 5e-5, n
 
 
+@pytest.mark.parametrize("stride", [1, 2, 3])
+def test_fused_edge_kernels_every_candidate_subset(backend, stride):
+    """k_edge_fwd / k_edge_bwd run all enabled depthwise candidates of an edge in one pass: every non-empty subset of
+    {sep_conv_15, sep_conv_9, dil_conv_15, dil_conv_9} (P-DARTS / CWP pruning leaves arbitrary ones) against the oracle."""
+    B, C, L = 3, 8, 70
+    torch.manual_seed(11 + stride)
+    x0 = torch.randn(B, C, L)
+    for sub in range(1, 16):
+        switch = [False] * 9
+        for v in range(4):
+            switch[4 + v] = bool(sub >> v & 1)
+        m = G.MixedOp(C, stride, switch, 0.0)
+        P = O.synthetic_params(_shapes(m, "cell_ops.0."), 100 + sub)
+        m.load_state_dict({k[len("cell_ops.0."):]: v for k, v in P.items()})
+        m.to(backend).train()
+        w0 = torch.softmax(torch.randn(sum(switch)), 0)
+        x, w = leaf(x0, backend), leaf(w0, backend)
+        y = m(x, w)
+        gy = torch.randn(y.shape)
+        (y * gy.to(backend)).sum().backward()
+        yo, xo, wo, Q = _oracle_mixed(m, x0, w0, switch, stride, P)
+        (yo * gy.double()).sum().backward()
+        assert relerr(y, yo) < 1e-5, sub
+        assert relerr(x.grad, xo.grad) < 5e-5, sub
+        assert relerr(w.grad, wo.grad) < 5e-5, sub
+        for n, p in m.named_parameters():
+            assert relerr(p.grad, Q["cell_ops.0." + n].grad) < 5e-5, (sub, n)
+
+
 def test_skip_connect_dropout_pdarts(backend):
     """P-DARTS: Identity -> Dropout(p) (model_discCNN.py:60-61).  The mask is drawn by the module; the kernels
     must apply exactly that mask in forward, dX and dmix."""
@@ -218,3 +247,20 @@ def test_wide_search_cell_matches_oracle(backend):
     assert relerr(al.grad, alo.grad) < 5e-5
     for n, p in m.named_parameters():
         assert relerr(p.grad, Q["cells.0." + n].grad) < 5e-5, n
+
+
+def test_compact_base_codes_input(backend):
+    """uint8 base codes [B, L] (0..3, 255 = N) expanded on the device give the same one-hot tensor the reference's loader
+    builds on the host, and the supernet takes them as input."""
+    torch.manual_seed(2)
+    B, L = 3, 37
+    codes = torch.randint(0, 4, (B, L))
+    codes[0, 5] = 255
+    x = torch.zeros(B, 4, L)
+    for b in range(B):
+        for l in range(L):
+            if codes[b, l] < 4:
+                x[b, codes[b, l], l] = 1.0
+    enc = G.encode_onehot(x)
+    assert torch.equal(enc, codes.to(torch.uint8))
+    assert torch.equal(G.expand_onehot(enc.to(backend)).cpu(), x)
